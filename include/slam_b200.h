@@ -1,0 +1,196 @@
+/*
+ * slam_b200.h -- C ABI of libslam_b200.so, the B200 (sm_100a) engine for the SLAM
+ * template-evaluation hot path.
+ *
+ * The reference (Pitt-JonesLab/slam_decomposition) is pure Python and has no FFI; the seam this
+ * library replaces is the set of duck-typed Python calls TemplateOptimizer makes on its basis /
+ * objective objects.  Each entry point below names the reference call
+ * site(s) it replaces (paths relative to the reference root).  The Python package
+ * `slam_decomposition_b200` binds these with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every pointer marked [dev] is a CUDA device pointer to caller-owned, contiguous memory
+ *     (e.g. torch.Tensor.data_ptr()); the library never frees or retains it.
+ *   - `desc` pointers are HOST pointers to a POD descriptor, read during the call only.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ *     asynchronous on that stream unless stated otherwise, re-entrant, and keep no global state.
+ *   - complex128 values are (re, im) pairs of doubles; 4x4 matrices are row-major, 32 doubles.
+ *   - return value: 0 = ok, negative = SlamStatus error (no exception crosses the ABI).
+ *   - parameter vectors (`x`, `grad`) are in the reference's API order: the order of
+ *     `QuantumCircuit.parameters`, i.e. sorted by name (basis.py:113-116); the descriptor carries
+ *     the index tables, so kernels read API-ordered vectors directly.
+ */
+#ifndef SLAM_B200_H
+#define SLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLAM_ABI_VERSION 1
+#define SLAM_MAX_K 8      /* max 2Q-gate applications per template (reference uses <= 6)       */
+#define SLAM_MAX_SLOTS 24 /* max scalar slots of one 2Q gate (smush1q: 8 + 2T + 1, T <= 7)     */
+#define SLAM_MAX_PARAMS 256
+
+typedef enum SlamStatus {
+  SLAM_OK = 0,
+  SLAM_ERR_INVALID = -1,     /* bad descriptor / argument (reference: ValueError)              */
+  SLAM_ERR_UNSUPPORTED = -2, /* valid but not implemented for this gate kind                   */
+  SLAM_ERR_CUDA = -3,        /* CUDA runtime error; see slam_last_cuda_error()                 */
+  SLAM_ERR_NO_DEVICE = -4
+} SlamStatus;
+
+/* 2Q basis-gate families (src/slam/utils/gates/custom_gates.py) */
+typedef enum SlamGateKind {
+  SLAM_GATE_RISWAP = 0,        /* RiSwapGate(alpha)                         custom_gates.py:582-595 */
+  SLAM_GATE_CG = 1,            /* ConversionGainGate(phi_c,phi_g,gc,gg,t)   custom_gates.py:163-184 */
+  SLAM_GATE_SMUSH = 2,         /* ConversionGainSmushGate(phi_c,phi_g,gc,gg,gx[T],gy[T],t) :215-250 */
+  SLAM_GATE_SMUSH_1QPHASE = 3, /* ConversionGainSmush1QPhaseGate(phi_a,phi_b,phi_c,phi_g,gc,gg,gz1,gz2,gx[T],gy[T],t) :260-306 */
+  SLAM_GATE_FIXED = 4          /* constant 4x4 (CanonicalGate, BerkeleyGate, any UnitaryGate)       */
+} SlamGateKind;
+
+/* cost functionals (src/slam/cost_function.py) evaluated from T = Tr(V^dag U) */
+typedef enum SlamCostKind {
+  SLAM_COST_BASIC = 0,         /* BasicCost        1 - |T|/4           cost_function.py:140-145 */
+  SLAM_COST_SQUARE = 1,        /* SquareCost       1 - (|T|^2+4)/20    cost_function.py:169-173 */
+  SLAM_COST_BASIC_INVERSE = 2  /* BasicCostInverse |T|/4               cost_function.py:133-137 */
+} SlamCostKind;
+
+/*
+ * Template structure after `basis.build(k)`: 1Q layer 0, then k x (2Q gate, 1Q layer).
+ * Replaces CircuitTemplate.__init__/build/_build_cycle (basis.py:52-93,124-169) and the V2 twin
+ * (basisv2.py:27-299), which hold the same information as a qiskit QuantumCircuit.
+ */
+typedef struct SlamTemplateDesc {
+  int32_t gate_kind;      /* SlamGateKind                                                        */
+  int32_t k;              /* number of 2Q gate applications, 1..SLAM_MAX_K                        */
+  int32_t T;              /* time slices of a smush gate (len(gx)); 0 otherwise                   */
+  int32_t n_slots;        /* scalar slots per 2Q gate (1, 5, 5+2T, 9+2T, 0)                       */
+  int32_t n_params;       /* P = len(Xk)                                                          */
+  int32_t no_exterior_1q; /* informational; absent layers are marked by p1q = -1                  */
+  int32_t vz_only;        /* 1: 1Q gates are RZ(lam) (basisv2.py:267-272); p1q[i][0], p1q[i][3]   */
+  int32_t reserved;
+  /* p1q[i][0..2] = Xk index of (theta,phi,lam) of the U gate on qubit 0 in layer i,
+     p1q[i][3..5] = same for qubit 1; -1 in [i][0] and [i][3] = that 1Q gate is absent.          */
+  int32_t p1q[SLAM_MAX_K + 1][6];
+  /* slot_param[g][s] = Xk index bound to slot s of the g-th 2Q gate, or -1 if the slot is the
+     constant slot_const[g][s].                                                                  */
+  int32_t slot_param[SLAM_MAX_K][SLAM_MAX_SLOTS];
+  double slot_const[SLAM_MAX_K][SLAM_MAX_SLOTS];
+  double fixed_gate[32];  /* SLAM_GATE_FIXED: the matrix, row-major (re,im)                       */
+} SlamTemplateDesc;
+
+/* ---- housekeeping ------------------------------------------------------------------------- */
+int slam_abi_version(void);
+const char* slam_status_string(int status);
+const char* slam_last_cuda_error(void); /* thread-local text of the last CUDA failure           */
+int slam_device_count(void);
+int slam_set_device(int device); /* cudaSetDevice for the calling thread (one process per GPU)   */
+
+/*
+ * K1  U[b] = template(x[b])                                  [B,4,4] complex128
+ * Replaces CircuitTemplate.eval / assign_Xk + qiskit Operator(circuit).data (basis.py:102-116),
+ * CircuitTemplateV2.eval (basisv2.py:143-145), and every gate __array__ they reach.
+ *   x   [dev] double[B, ldx]  (ldx >= n_params, row b at x + b*ldx)
+ *   U   [dev] double[B, 32]
+ */
+int slam_template_eval(const SlamTemplateDesc* desc, const double* x, int64_t ldx, double* U, int64_t B,
+                       void* stream);
+
+/*
+ * K2  loss[b], grad[b,:] of cost(template(x[b]), V[tgt[b]])  -- the unit of the headline metric.
+ * Replaces objective_func (optimizer.py:191-214) = basis.eval + objective.unitary_fidelity
+ * (cost_function.py:133-173) and scipy's (P+1)-evaluation finite-difference gradient
+ * (opt.minimize(jac=None), optimizer.py:270-278) by one analytic adjoint pass.
+ *   V       [dev] double[Nt, 32]   targets
+ *   tgt_idx [dev] int32[B] or NULL (NULL: target of row b is b % Nt)
+ *   loss    [dev] double[B]
+ *   grad    [dev] double[B, ldg] or NULL (loss only)
+ *   trace   [dev] double[B, 2]  or NULL: T = Tr(V^dag U)
+ */
+int slam_loss_grad(const SlamTemplateDesc* desc, const double* x, int64_t ldx, const double* V, int64_t Nt,
+                   const int32_t* tgt_idx, int32_t cost_kind, double* loss, double* grad, int64_t ldg,
+                   double* trace, int64_t B, void* stream);
+
+/*
+ * K3  Weyl-chamber coordinates and Makhlin invariants of a batch of 4x4 unitaries.
+ * Replaces weylchamber.c1c2c3 / g1g2g3 as called from basis_abc.py:80-84, optimizer.py:85,103,224,
+ * cost_function.py:199-221, parallel_drive_volume.py:225, pd_playground.py:199.
+ *   U [dev] double[B,32];  c [dev] double[B,3] or NULL;  g [dev] double[B,3] or NULL
+ */
+#define SLAM_WEYL_FOLD 1   /* c1 > 1/2 -> 1 - c1 (pd_playground.py:199-202)                      */
+#define SLAM_WEYL_ROUND8 2 /* round to 8 decimals as weylchamber does                            */
+int slam_weyl(const double* U, int64_t B, double* c, double* g, int32_t flags, void* stream);
+
+/*
+ * K5  Batched, device-resident L-BFGS over (target, restart) pairs for ONE template size k.
+ * Replaces the restart loop around opt.minimize(method="BFGS") (optimizer.py:253-295); the caller
+ * (TemplateOptimizer._run shim) iterates k ascending and carries `best_loss` across calls, which
+ * reproduces the k-loop early exit (optimizer.py:233,297-303).
+ */
+typedef struct SlamOptOpts {
+  int32_t max_iter;      /* per restart; reference: options={"maxiter": 2500}                    */
+  int32_t history;       /* L-BFGS pairs kept (<= 8); 0 = auto from shared-memory budget         */
+  int32_t cost_kind;     /* SlamCostKind                                                         */
+  int32_t early_exit;    /* 1: other restarts of a target stop once one is < success_threshold   */
+  double success_threshold; /* reference SUCCESS_THRESHOLD = 1e-10 (optimizer.py:18)             */
+  double f_stop;         /* stop a restart once loss < f_stop (polish below the threshold)       */
+  double gtol;           /* stop when max|g| < gtol ...                                          */
+  double gtol_far;       /* ... or max|g| < gtol_far while loss > f_far (a non-zero local min)   */
+  double f_far;
+  double x0_lo, x0_hi;   /* when x0 == NULL: x0 ~ U[x0_lo, x0_hi) from Philox(seed)              */
+} SlamOptOpts;
+
+void slam_opt_defaults(SlamOptOpts* o);
+
+/*
+ *   V          [dev] double[Nt,32] targets
+ *   x0         [dev] double[Nt, restarts, ldx0] or NULL (then Philox4x32-10 keyed by seed)
+ *   active     [dev] int32[Nt] or NULL: targets with active[t] == 0 are skipped (already solved)
+ *   out_loss   [dev] double[Nt, restarts]   final loss of every restart (+inf if skipped/aborted)
+ *   out_x      [dev] double[Nt, restarts, P] final parameters of every restart
+ *   out_iters  [dev] int32 [Nt, restarts]   L-BFGS iterations used
+ *   out_evals  [dev] int64 [1] or NULL      += number of loss+grad evaluations performed
+ */
+int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
+                     const double* x0, int64_t ldx0, uint64_t seed, const int32_t* active,
+                     const SlamOptOpts* opts, double* out_loss, double* out_x, int32_t* out_iters,
+                     unsigned long long* out_evals, void* stream);
+
+/*
+ * K6  Fused coverage-set Monte-Carlo: Philox -> params -> template -> c1c2c3 -> fold -> bin.
+ * Replaces the N-iteration loop of parallel_drive_volume.py:209-225 and the mirror fold :292-307.
+ *   params[j] = lo + (hi - lo) * u53(seed, sample, j)   (j in API order; see oracle.philox_uniform)
+ *   hist   [dev] int64[nbins^3]  (+= counts; caller zeroes)   bins over folded [0,1/2]^3
+ *   coords [dev] double[n_samples,3] or NULL: un-rounded folded coordinates of every sample
+ */
+int slam_coverage_mc(const SlamTemplateDesc* desc, uint64_t seed, int64_t first_sample, int64_t n_samples,
+                     double lo, double hi, int32_t nbins, unsigned long long* hist, double* coords,
+                     void* stream);
+
+/*
+ * K4b Weyl trajectory of a parallel-driven gate: N slices of ConversionGainSmush1QPhase, R
+ * sub-times each, as a prefix product.  Replaces ParallelDrivenGateWidget.iterate_time / solve_end
+ * (pd_playground.py:169-208).  One trajectory per batch row.
+ *   gate   [dev] double[B, 8]  (phi_a,phi_b,phi_c,phi_g,gc,gg,gz1,gz2)
+ *   gx,gy  [dev] double[B, N]
+ *   coords [dev] double[B, N, R, 3] (folded; flags as slam_weyl) or NULL
+ *   Ufinal [dev] double[B, 32] or NULL
+ */
+int slam_pd_trajectory(const double* gate, const double* gx, const double* gy, int32_t N, int32_t R, double dt,
+                       int32_t flags, double* coords, double* Ufinal, int64_t B, void* stream);
+
+/*
+ * Diagnostic: register-resident DFMA loop; writes achieved FP64 FLOP/s of the current device to
+ * *flops (host pointer).  Synchronous.  Used as the roofline denominator (MEASURED_PEAKS.json has
+ * no FP64 figure).
+ */
+int slam_fp64_peak(int32_t iters, double* flops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAM_B200_H */

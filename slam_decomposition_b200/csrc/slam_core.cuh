@@ -1,0 +1,491 @@
+// slam_core.cuh -- device core shared by the eval / loss+grad / L-BFGS / coverage kernels.
+//
+// Work decomposition ("team" design):
+//   a template evaluation is a chain U = L_k G_{k-1} L_{k-1} ... G_0 L_0 of 4x4 complex128 matrices.
+//   One problem is handled by a TEAM of LPP lanes (LPP = 1, 2 or 4) of one warp.  Each lane owns
+//   CPL = 4/LPP columns of the running right-product R_i and the matching rows of the running
+//   left-product W_i, so every matrix product in both sweeps is a lane-local 4-vector update and
+//   only scalar reductions (the trace, the per-layer partial derivatives) cross lanes by shuffle.
+//   The backward sweep is a reversible adjoint: because every factor is unitary, R_i is recovered
+//   from R_{i+1} by multiplying with the adjoint factors, so nothing is stored per layer.
+//
+// Reference behaviour restated here (paths relative to the reference root):
+//   layer/gate order ........ src/slam/basis.py:152-169, src/slam/basisv2.py:262-299
+//   U3 / RZ matrices ........ qiskit UGate / RZGate (reached from basis.py:157,168; basisv2.py:267-298)
+//   RiSwap .................. src/slam/utils/gates/custom_gates.py:582-595
+//   ConversionGain .......... custom_gates.py:163-184 -> src/slam/hamiltonian.py:84-111 (closed form)
+//   cost functionals ........ src/slam/cost_function.py:133-173
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slam_b200.h"
+
+namespace slam {
+
+// ------------------------------------------------------------------------------------------------
+// kernel-side template descriptor (built on the host from SlamTemplateDesc, passed by value)
+// ------------------------------------------------------------------------------------------------
+enum GateMode : int {
+  GM_SYM = 0,    // constant gate [[co,0,0,i so],[0,ci,i si,0],[0,i si,ci,0],[i so,0,0,co]] (RiSwap, CG with zero phases)
+  GM_BLOCK = 1,  // two 2x2 blocks with complex off-diagonals; constant or bound to parameters
+  GM_DENSE = 2,  // constant dense 4x4 per repetition (fixed gates, constant smush gates)
+  GM_SMUSH = 3   // parameter-bound smush gate: per-slice exp(-i dt H) (forward evaluation only)
+};
+
+struct KTemplate {
+  int k;         // 2Q gate applications
+  int P;         // parameters
+  int gmode;     // GateMode
+  int gate_kind; // SlamGateKind
+  int T;         // smush slices
+  int n_slots;
+  int vz_only;
+  int n_trig;    // entries of the per-problem trig cache: 6(k+1) [+ 4k for parameter-bound block gates]
+  int gate_bound[SLAM_MAX_K];        // GM_BLOCK: 1 if any slot of gate g is a parameter
+  short p1q[SLAM_MAX_K + 1][6];
+  short slot_param[SLAM_MAX_K][SLAM_MAX_SLOTS];
+  double slot_const[SLAM_MAX_K][SLAM_MAX_SLOTS];
+  double gsym[SLAM_MAX_K][4];        // GM_SYM: co, so, ci, si
+  double gblk[SLAM_MAX_K][8];        // GM_BLOCK constant gates: (cos,sin) of phi_c, phi_g, a_c, a_g
+  double dense[SLAM_MAX_K][32];      // GM_DENSE
+};
+
+// ------------------------------------------------------------------------------------------------
+// complex helpers (plain structs; everything lives in registers)
+// ------------------------------------------------------------------------------------------------
+struct cd {
+  double re, im;
+};
+__device__ __forceinline__ cd mkc(double r, double i) { return cd{r, i}; }
+__device__ __forceinline__ cd cmul(cd a, cd b) { return cd{fma(a.re, b.re, -(a.im * b.im)), fma(a.re, b.im, a.im * b.re)}; }
+__device__ __forceinline__ cd cmulc(cd a, cd b) {  // a * conj(b)
+  return cd{fma(a.re, b.re, a.im * b.im), fma(a.im, b.re, -(a.re * b.im))};
+}
+__device__ __forceinline__ void cacc(cd& acc, cd a, cd b) {  // acc += a*b
+  acc.re = fma(a.re, b.re, fma(-a.im, b.im, acc.re));
+  acc.im = fma(a.re, b.im, fma(a.im, b.re, acc.im));
+}
+// m*a + n*b, optionally with m and n conjugated
+template <bool CONJ>
+__device__ __forceinline__ cd lin2(cd m, cd a, cd n, cd b) {
+  cd o;
+  if (!CONJ) {
+    o.re = fma(m.re, a.re, fma(-m.im, a.im, fma(n.re, b.re, -(n.im * b.im))));
+    o.im = fma(m.re, a.im, fma(m.im, a.re, fma(n.re, b.im, n.im * b.re)));
+  } else {
+    o.re = fma(m.re, a.re, fma(m.im, a.im, fma(n.re, b.re, n.im * b.im)));
+    o.im = fma(m.re, a.im, fma(-m.im, a.re, fma(n.re, b.im, -(n.im * b.re))));
+  }
+  return o;
+}
+
+enum { OP_N = 0, OP_T = 1, OP_H = 2 };  // apply M, M^T, M^dagger
+
+// v <- (op M acting on qubit Q) v  for a 4-vector indexed (q1 q0); m = {m00, m01, m10, m11}
+template <int Q, int OP>
+__device__ __forceinline__ void apply1q(cd v[4], const cd m[4]) {
+  const cd e01 = (OP == OP_N) ? m[1] : m[2];
+  const cd e10 = (OP == OP_N) ? m[2] : m[1];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int lo = (Q == 0) ? 2 * p : p;
+    const int hi = (Q == 0) ? 2 * p + 1 : p + 2;
+    const cd a = v[lo], b = v[hi];
+    v[lo] = lin2<OP == OP_H>(m[0], a, e01, b);
+    v[hi] = lin2<OP == OP_H>(e10, a, m[3], b);
+  }
+}
+
+// 1Q gate matrices from cached (cos, sin) pairs
+__device__ __forceinline__ void build_u3(double2 t, double2 p, double2 l, cd m[4]) {
+  // t = (cos, sin)(theta/2), p = (cos, sin)(phi), l = (cos, sin)(lam)
+  m[0] = mkc(t.x, 0.0);
+  m[1] = mkc(-(l.x * t.y), -(l.y * t.y));
+  m[2] = mkc(p.x * t.y, p.y * t.y);
+  const double er = fma(p.x, l.x, -(p.y * l.y)), ei = fma(p.y, l.x, p.x * l.y);
+  m[3] = mkc(er * t.x, ei * t.x);
+}
+__device__ __forceinline__ void build_rz(double2 h, cd m[4]) {  // h = (cos, sin)(lam/2)
+  m[0] = mkc(h.x, -h.y);
+  m[1] = mkc(0.0, 0.0);
+  m[2] = mkc(0.0, 0.0);
+  m[3] = mkc(h.x, h.y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2Q gates
+// ------------------------------------------------------------------------------------------------
+struct BlockGate {  // G[0,0]=G[3,3]=co, G[0,3]=bo, G[3,0]=go, G[1,1]=G[2,2]=ci, G[1,2]=bi, G[2,1]=gi
+  double co, ci;
+  cd bo, go, bi, gi;
+};
+
+// from (cos,sin) of phi_c, phi_g, a_c = gc*t, a_g = gg*t  (closed form of exp(-i t (gc H_c + gg H_g)))
+__device__ __forceinline__ BlockGate block_from_trig(double2 pc, double2 pg, double2 ac, double2 ag) {
+  BlockGate g;
+  g.co = ag.x;
+  g.ci = ac.x;
+  g.bi = mkc(-(pc.y * ac.y), -(pc.x * ac.y));  // -i e^{-i phi_c} sin a_c
+  g.gi = mkc(pc.y * ac.y, -(pc.x * ac.y));     // -i e^{+i phi_c} sin a_c
+  g.bo = mkc(-(pg.y * ag.y), -(pg.x * ag.y));
+  g.go = mkc(pg.y * ag.y, -(pg.x * ag.y));
+  return g;
+}
+
+template <int OP>
+__device__ __forceinline__ void block_apply(cd v[4], const BlockGate& g) {
+  const cd b_o = (OP == OP_N) ? g.bo : g.go;  // effective [0,3]
+  const cd g_o = (OP == OP_N) ? g.go : g.bo;  // effective [3,0]
+  const cd b_i = (OP == OP_N) ? g.bi : g.gi;
+  const cd g_i = (OP == OP_N) ? g.gi : g.bi;
+  const cd v0 = v[0], v1 = v[1], v2 = v[2], v3 = v[3];
+  constexpr bool C = (OP == OP_H);
+  v[0] = lin2<C>(mkc(g.co, 0.0), v0, b_o, v3);
+  v[3] = lin2<C>(g_o, v0, mkc(g.co, 0.0), v3);
+  v[1] = lin2<C>(mkc(g.ci, 0.0), v1, b_i, v2);
+  v[2] = lin2<C>(g_i, v1, mkc(g.ci, 0.0), v2);
+}
+
+// symmetric gate with purely imaginary off-diagonals: G = G^T, G^dagger = conj(G)
+template <int OP>
+__device__ __forceinline__ void sym_apply(cd v[4], double co, double so, double ci, double si) {
+  if (OP == OP_H) {
+    so = -so;
+    si = -si;
+  }
+  const cd v0 = v[0], v1 = v[1], v2 = v[2], v3 = v[3];
+  v[0] = mkc(fma(co, v0.re, -(so * v3.im)), fma(co, v0.im, so * v3.re));
+  v[3] = mkc(fma(co, v3.re, -(so * v0.im)), fma(co, v3.im, so * v0.re));
+  v[1] = mkc(fma(ci, v1.re, -(si * v2.im)), fma(ci, v1.im, si * v2.re));
+  v[2] = mkc(fma(ci, v2.re, -(si * v1.im)), fma(ci, v2.im, si * v1.re));
+}
+
+template <int OP>
+__device__ __forceinline__ void dense_apply(cd v[4], const double* __restrict__ g) {  // g: 32 doubles row-major
+  cd o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    cd acc = mkc(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = (OP == OP_N) ? (i * 4 + j) : (j * 4 + i);
+      const cd m = mkc(g[2 * e], (OP == OP_H) ? -g[2 * e + 1] : g[2 * e + 1]);
+      cacc(acc, m, v[j]);
+    }
+    o[i] = acc;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = o[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// team reductions
+// ------------------------------------------------------------------------------------------------
+template <int LPP>
+__device__ __forceinline__ double team_sum(double v) {
+  if (LPP >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+  if (LPP >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+template <int LPP>
+__device__ __forceinline__ double team_max(double v) {
+  if (LPP >= 2) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  if (LPP >= 4) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trig cache: entry e < 6(k+1): layer e/6, slot e%6 (q0: theta/2, phi, lam; q1: theta/2, phi, lam)
+//             entries 6(k+1)+4g+{0,1,2,3}: gate g: phi_c, phi_g, a_c, a_g   (parameter-bound block gates)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double slot_value(const KTemplate& kt, const double* xs, int g, int s) {
+  const int p = kt.slot_param[g][s];
+  return p >= 0 ? xs[p] : kt.slot_const[g][s];
+}
+
+template <int LPP>
+__device__ __forceinline__ void fill_trig(const KTemplate& kt, const double* xs, double2* tg, int sub) {
+  const int n1 = 6 * (kt.k + 1);
+  for (int e = sub; e < kt.n_trig; e += LPP) {
+    double2 cs = make_double2(1.0, 0.0);
+    if (e < n1) {
+      const int layer = e / 6, s = e - 6 * layer;
+      const int p = kt.p1q[layer][s];
+      if (p >= 0) {
+        const bool half = kt.vz_only ? true : (s == 0 || s == 3);
+        const double a = half ? 0.5 * xs[p] : xs[p];
+        sincos(a, &cs.y, &cs.x);
+      }
+    } else {
+      const int q = e - n1;
+      const int g = q >> 2, w = q & 3;
+      if (kt.gate_kind == SLAM_GATE_RISWAP) {
+        // RiSwap(alpha) in block form: phi_c = pi (so that -i e^{-i phi_c} = +i), a_c = pi*alpha/2, a_g = 0
+        if (w == 0) cs = make_double2(-1.0, 0.0);
+        if (w == 2) sincos(1.5707963267948966 * slot_value(kt, xs, g, 0), &cs.y, &cs.x);
+      } else {  // SLAM_GATE_CG slots: phi_c, phi_g, gc, gg, t
+        double a;
+        if (w == 0) a = slot_value(kt, xs, g, 0);
+        else if (w == 1) a = slot_value(kt, xs, g, 1);
+        else if (w == 2) a = slot_value(kt, xs, g, 2) * slot_value(kt, xs, g, 4);
+        else a = slot_value(kt, xs, g, 3) * slot_value(kt, xs, g, 4);
+        sincos(a, &cs.y, &cs.x);
+      }
+    }
+    tg[e] = cs;
+  }
+}
+
+// block gate g of this problem: from the trig cache if parameter-bound, else from the constant table
+__device__ __forceinline__ BlockGate load_block(const KTemplate& kt, const double2* tg, int g) {
+  if (kt.gate_bound[g]) {
+    const double2* q = tg + 6 * (kt.k + 1) + 4 * g;
+    return block_from_trig(q[0], q[1], q[2], q[3]);
+  }
+  const double* c = kt.gblk[g];
+  return block_from_trig(make_double2(c[0], c[1]), make_double2(c[2], c[3]), make_double2(c[4], c[5]),
+                         make_double2(c[6], c[7]));
+}
+
+template <int GM, int OP>
+__device__ __forceinline__ void gate_apply(const KTemplate& kt, const BlockGate& bg, int g, cd v[4]) {
+  if (GM == GM_SYM) sym_apply<OP>(v, kt.gsym[g][0], kt.gsym[g][1], kt.gsym[g][2], kt.gsym[g][3]);
+  else if (GM == GM_BLOCK) block_apply<OP>(v, bg);
+  else dense_apply<OP>(v, kt.dense[g]);
+}
+
+__device__ __forceinline__ bool build_layer(const KTemplate& kt, const double2* tg, int i, cd A[4], cd B[4]) {
+  // returns false if the layer is absent (no_exterior_1q); A acts on qubit 1 (high bit), B on qubit 0
+  if (kt.p1q[i][0] < 0 && kt.p1q[i][3] < 0) return false;
+  const double2* t = tg + 6 * i;
+  if (kt.vz_only) {
+    build_rz(t[0], B);
+    build_rz(t[3], A);
+  } else {
+    build_u3(t[0], t[1], t[2], B);
+    build_u3(t[3], t[4], t[5], A);
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward sweep: r[c] = column (sub*CPL + c) of U(x)
+// ------------------------------------------------------------------------------------------------
+template <int LPP, int GM>
+__device__ __forceinline__ void forward_chain(const KTemplate& kt, const double2* tg, int sub, cd r[4 / LPP][4]) {
+  constexpr int CPL = 4 / LPP;
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) r[c][a] = mkc((a == sub * CPL + c) ? 1.0 : 0.0, 0.0);
+  for (int i = 0; i <= kt.k; ++i) {
+    cd A[4], B[4];
+    if (build_layer(kt, tg, i, A, B)) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        apply1q<0, OP_N>(r[c], B);
+        apply1q<1, OP_N>(r[c], A);
+      }
+    }
+    if (i < kt.k) {
+      BlockGate bg;
+      if (GM == GM_BLOCK) bg = load_block(kt, tg, i);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_N>(kt, bg, i, r[c]);
+    }
+  }
+}
+
+// cost functional from |T|: value and d(loss)/d|T|   (src/slam/cost_function.py:133-173)
+__device__ __forceinline__ void cost_from_abs(int cost_kind, double a, double& loss, double& dl_da) {
+  if (cost_kind == SLAM_COST_SQUARE) {
+    loss = 1.0 - (a * a + 4.0) / 20.0;
+    dl_da = -a / 10.0;
+  } else if (cost_kind == SLAM_COST_BASIC_INVERSE) {
+    loss = a * 0.25;
+    dl_da = 0.25;
+  } else {
+    loss = 1.0 - a * 0.25;
+    dl_da = -0.25;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss + analytic gradient for one problem, executed by a team.
+//   xs : this problem's parameters (API order)            [shared or global]
+//   tg : this problem's trig cache, n_trig entries        [shared]  (filled here)
+//   gs : this problem's gradient (API order), written if WANT_GRAD
+//   vcol[c][a] = V[a][sub*CPL + c]  (this lane's target columns)
+// returns loss (identical on every lane of the team); *T_out = Tr(V^dag U)
+// ------------------------------------------------------------------------------------------------
+template <int LPP, int GM, bool WANT_GRAD>
+__device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const double* xs, double2* tg, double* gs,
+                                                 const cd vcol[4 / LPP][4], int cost_kind, int sub, cd* T_out) {
+  constexpr int CPL = 4 / LPP;
+  fill_trig<LPP>(kt, xs, tg, sub);
+  if (WANT_GRAD)
+    for (int j = sub; j < kt.P; j += LPP) gs[j] = 0.0;
+  __syncwarp();
+
+  cd r[CPL][4];
+  forward_chain<LPP, GM>(kt, tg, sub, r);
+
+  // T = Tr(V^dag U) = sum_col sum_a conj(V[a][col]) U[a][col]
+  cd Tp = mkc(0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      Tp.re = fma(vcol[c][a].re, r[c][a].re, fma(vcol[c][a].im, r[c][a].im, Tp.re));
+      Tp.im = fma(vcol[c][a].re, r[c][a].im, fma(-vcol[c][a].im, r[c][a].re, Tp.im));
+    }
+  cd T = mkc(team_sum<LPP>(Tp.re), team_sum<LPP>(Tp.im));
+  const double absT = sqrt(fma(T.re, T.re, T.im * T.im));
+  double loss, dl_da;
+  cost_from_abs(cost_kind, absT, loss, dl_da);
+  if (T_out) *T_out = T;
+  if (!WANT_GRAD) return loss;
+
+  // w[c] = row (sub*CPL+c) of (dl/d|T|) * conj(T)/|T| * V^dagger ; d loss = Re( sum w dM r )
+  const double inv = absT > 0.0 ? dl_da / absT : 0.0;
+  const cd ph = mkc(T.re * inv, -T.im * inv);
+  cd w[CPL][4];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) w[c][a] = cmulc(ph, vcol[c][a]);
+
+  for (int i = kt.k; i >= 0; --i) {
+    cd A[4], B[4];
+    if (build_layer(kt, tg, i, A, B)) {
+      cd EA[4], EB[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) EA[e] = EB[e] = mkc(0.0, 0.0);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        apply1q<1, OP_H>(r[c], A);  // r <- L_i^dagger r : columns of R_i
+        apply1q<0, OP_H>(r[c], B);
+        cd v[4], u[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          v[a] = r[c][a];
+          u[a] = w[c][a];
+        }
+        apply1q<0, OP_N>(v, B);  // v = (I (x) B) r
+        apply1q<1, OP_T>(u, A);  // u = w (A (x) I)
+        // EA[a][a'] = sum_b w[(a,b)] v[(a',b)] ; EB[b][b'] = sum_a' u[(a',b)] r[(a',b')]
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              cacc(EA[a * 2 + a2], w[c][2 * a + b], v[2 * a2 + b]);
+              cacc(EB[a * 2 + a2], u[2 * b + a], r[c][2 * b + a2]);
+            }
+        apply1q<0, OP_T>(u, B);  // w <- w L_i
+#pragma unroll
+        for (int a = 0; a < 4; ++a) w[c][a] = u[a];
+      }
+      // partial derivatives of this lane, then team sum
+      const double2* t = tg + 6 * i;
+      double d[6];
+      if (kt.vz_only) {
+        // RZ = diag(e^{-i l/2}, e^{+i l/2}); d/dl = (i/2) diag(-e^{-i l/2}, e^{+i l/2})
+        // Re(-(i/2) m00 E00 + (i/2) m11 E11) = 0.5 * (Im(m00 E00) - Im(m11 E11))
+        const cd b0 = cmul(B[0], EB[0]), b3 = cmul(B[3], EB[3]);
+        const cd a0 = cmul(A[0], EA[0]), a3 = cmul(A[3], EA[3]);
+        d[0] = 0.5 * (b0.im - b3.im);
+        d[3] = 0.5 * (a0.im - a3.im);
+        d[1] = d[2] = d[4] = d[5] = 0.0;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const cd* M = q == 0 ? B : A;
+          const cd* E = q == 0 ? EB : EA;
+          const double ch = t[3 * q].x, sh = t[3 * q].y;  // cos, sin of theta/2
+          // M01 = -e^{il} s, M10 = e^{ip} s, M11 = e^{i(p+l)} c.  With t01 = e^{il}E01 etc:
+          //  d/dtheta = 0.5*( -s Re(E00) - c Re(t01) + c Re(t10) - s Re(t11) )
+          //  d/dphi   = Re(i (M10 E10 + M11 E11)) = -Im(M10 E10 + M11 E11)
+          //  d/dlam   = Re(i (M01 E01 + M11 E11)) = -Im(M01 E01 + M11 E11)
+          const cd m01e = cmul(M[1], E[1]), m10e = cmul(M[2], E[2]), m11e = cmul(M[3], E[3]);
+          // e^{il}E01 = -M01E01/s ... avoid the division: use trig directly
+          const double2 pp = t[3 * q + 1], ll = t[3 * q + 2];
+          const cd t01 = cmul(mkc(ll.x, ll.y), E[1]);
+          const cd t10 = cmul(mkc(pp.x, pp.y), E[2]);
+          const double er = fma(pp.x, ll.x, -(pp.y * ll.y)), ei = fma(pp.y, ll.x, pp.x * ll.y);
+          const cd t11 = cmul(mkc(er, ei), E[3]);
+          d[3 * q + 0] = 0.5 * (ch * (t10.re - t01.re) - sh * (E[0].re + t11.re));
+          d[3 * q + 1] = -(m10e.im + m11e.im);
+          d[3 * q + 2] = -(m01e.im + m11e.im);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 6; ++s) d[s] = team_sum<LPP>(d[s]);
+      if (sub == 0) {
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+          const int p = kt.p1q[i][s];
+          if (p >= 0) gs[p] += d[s];
+        }
+      }
+    }
+    if (i > 0) {
+      const int g = i - 1;
+      BlockGate bg;
+      if (GM == GM_BLOCK) bg = load_block(kt, tg, g);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_H>(kt, bg, g, r[c]);  // r <- G^dagger r
+      if (GM == GM_BLOCK && kt.gate_bound[g]) {
+        // environment of the gate: E[i][j] = sum_c w[c][i] r[c][j] on the block pattern
+        cd Ed_o = mkc(0, 0), Ed_i = mkc(0, 0), E03 = mkc(0, 0), E30 = mkc(0, 0), E12 = mkc(0, 0), E21 = mkc(0, 0);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          cacc(Ed_o, w[c][0], r[c][0]);
+          cacc(Ed_o, w[c][3], r[c][3]);
+          cacc(Ed_i, w[c][1], r[c][1]);
+          cacc(Ed_i, w[c][2], r[c][2]);
+          cacc(E03, w[c][0], r[c][3]);
+          cacc(E30, w[c][3], r[c][0]);
+          cacc(E12, w[c][1], r[c][2]);
+          cacc(E21, w[c][2], r[c][1]);
+        }
+        const double2* q = tg + 6 * (kt.k + 1) + 4 * g;
+        const double2 pc = q[0], pg = q[1], ac = q[2], ag = q[3];
+        // d/da_c: dci = -sin a_c ; dbi = -i e^{-i pc} cos a_c ; dgi = -i e^{+i pc} cos a_c
+        const cd dbi_a = mkc(-(pc.y * ac.x), -(pc.x * ac.x)), dgi_a = mkc(pc.y * ac.x, -(pc.x * ac.x));
+        const cd dbo_a = mkc(-(pg.y * ag.x), -(pg.x * ag.x)), dgo_a = mkc(pg.y * ag.x, -(pg.x * ag.x));
+        double d_ac = -ac.y * Ed_i.re + cmul(dbi_a, E12).re + cmul(dgi_a, E21).re;
+        double d_ag = -ag.y * Ed_o.re + cmul(dbo_a, E03).re + cmul(dgo_a, E30).re;
+        // d/dphi_c: dbi = -i*bi, dgi = +i*gi  -> Re(-i bi E12 + i gi E21) = Im(bi E12) - Im(gi E21)
+        double d_pc = cmul(bg.bi, E12).im - cmul(bg.gi, E21).im;
+        double d_pg = cmul(bg.bo, E03).im - cmul(bg.go, E30).im;
+        d_ac = team_sum<LPP>(d_ac);
+        d_ag = team_sum<LPP>(d_ag);
+        d_pc = team_sum<LPP>(d_pc);
+        d_pg = team_sum<LPP>(d_pg);
+        if (sub == 0) {
+          if (kt.gate_kind == SLAM_GATE_RISWAP) {
+            const int p = kt.slot_param[g][0];
+            if (p >= 0) gs[p] += 1.5707963267948966 * d_ac;
+          } else {
+            const double gc = slot_value(kt, xs, g, 2), gg = slot_value(kt, xs, g, 3), tt = slot_value(kt, xs, g, 4);
+            int p;
+            if ((p = kt.slot_param[g][0]) >= 0) gs[p] += d_pc;
+            if ((p = kt.slot_param[g][1]) >= 0) gs[p] += d_pg;
+            if ((p = kt.slot_param[g][2]) >= 0) gs[p] += tt * d_ac;
+            if ((p = kt.slot_param[g][3]) >= 0) gs[p] += tt * d_ag;
+            if ((p = kt.slot_param[g][4]) >= 0) gs[p] += gc * d_ac + gg * d_ag;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_T>(kt, bg, g, w[c]);  // w <- w G
+    }
+  }
+  __syncwarp();
+  return loss;
+}
+
+}  // namespace slam

@@ -1,0 +1,32 @@
+// slam_host.h -- host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "slam_core.cuh"
+
+namespace slam {
+
+void set_cuda_error(cudaError_t e, const char* where);
+
+#define SLAM_CUDA_CHECK(expr)                   \
+  do {                                          \
+    cudaError_t _e = (expr);                    \
+    if (_e != cudaSuccess) {                    \
+      ::slam::set_cuda_error(_e, #expr);        \
+      return SLAM_ERR_CUDA;                     \
+    }                                           \
+  } while (0)
+
+// Validate a SlamTemplateDesc and lower it to the kernel-side KTemplate.
+//   allow_bound_smush: parameter-bound smush gates are accepted (forward-only kernels)
+int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_smush);
+
+// Host evaluation of a *constant* smush gate is not done on the CPU: callers lower constant smush
+// gates to GM_DENSE by running the device smush kernel once (see slam_smush.cu).
+int lower_const_smush(const SlamTemplateDesc* d, KTemplate* kt, cudaStream_t stream);
+
+}  // namespace slam
