@@ -1,0 +1,384 @@
+// slam_lbfgs.cu -- K5: device-resident batched L-BFGS over (target, restart) problems.
+//
+// Replaces the restart loop around scipy.optimize.minimize(method="BFGS") (src/slam/optimizer.py:253-295):
+// instead of one Python-driven BFGS with (P+1)-evaluation finite-difference gradients per restart, every
+// (target, restart) pair is an independent problem solved by a TEAM of 4 lanes with analytic adjoint
+// gradients (slam_core.cuh).  All optimiser state of a problem -- x, g, trial point, direction, the L-BFGS
+// (s, y) history and the (cos, sin) cache -- lives in that team's slice of shared memory; nothing but the
+// final result touches HBM.  A persistent grid pulls problems from a global counter, so early exits and
+// uneven iteration counts do not leave SMs idle.
+//
+// Warp-level structure: each "tick" every team of the warp performs exactly one loss+gradient evaluation
+// (the expensive, fully convergent part), then runs its own cheap, possibly divergent, line-search /
+// history bookkeeping.
+#include <cfloat>
+
+#include "slam_host.h"
+#include "slam_philox.cuh"
+
+namespace slam {
+
+constexpr int LPP = 4;
+constexpr double kArmijo = 1e-4;
+
+struct LbfgsArgs {
+  const double* V;
+  const double* x0;
+  int64_t ldx0;
+  uint64_t seed;
+  const int32_t* active;
+  int64_t Nt;
+  int restarts;
+  int m;        // history length
+  int RS;       // doubles of shared memory per team
+  int max_iter;
+  int cost_kind;
+  int early_exit;
+  double success_threshold, f_stop, gtol, gtol_far, f_far, x0_lo, x0_span;
+  double* out_loss;
+  double* out_x;
+  int32_t* out_iters;
+  unsigned long long* out_evals;
+  unsigned long long* next;  // work counter
+  int32_t* solved;           // per-target flag (early exit)
+};
+
+__device__ __forceinline__ double tsum(double v, unsigned mask) {
+  v += __shfl_xor_sync(mask, v, 1);
+  v += __shfl_xor_sync(mask, v, 2);
+  return v;
+}
+__device__ __forceinline__ double tmax(double v, unsigned mask) {
+  v = fmax(v, __shfl_xor_sync(mask, v, 1));
+  v = fmax(v, __shfl_xor_sync(mask, v, 2));
+  return v;
+}
+
+enum { ST_IDLE = 0, ST_INIT = 1, ST_LS = 2 };
+
+template <int GM>
+__global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ KTemplate kt,
+                                                       const __grid_constant__ LbfgsArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  const int P = kt.P, m = A.m;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int team = tid >> 2, sub = tid & 3;
+  const unsigned tmask = 0xFu << (lane & ~3);
+  double* base = smem + (size_t)team * A.RS;
+  // two (x, g) buffers: buffer b holds x at base + 2bP and g at base + (2b+1)P
+  double* D = base + 4 * P;
+  double* S = base + 5 * P;
+  double* Y = S + m * P;
+  double* rho = Y + m * P;
+  double* alp = rho + m;
+  double2* tg = reinterpret_cast<double2*>(alp + m + ((5 * P) & 1));
+
+  const int64_t total = A.Nt * (int64_t)A.restarts;
+  // team-uniform scalars
+  int state = ST_IDLE, cur = 0, iter = 0, ls = 0, hcount = 0, hpos = 0;
+  int64_t pid = -1;
+  double f = 0.0, alpha = 1.0, gd = 0.0, gamma = 1.0, f_chk = 0.0;
+  bool slow = false;
+  unsigned long long evals = 0;
+  bool exhausted = false;
+  cd vcol[1][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) vcol[0][a] = mkc(0.0, 0.0);
+
+  while (true) {
+    // ---------------- fetch work for idle teams --------------------------------------------------
+    while (state == ST_IDLE && !exhausted) {
+      unsigned long long w = 0;
+      if (sub == 0) w = atomicAdd(A.next, 1ULL);
+      w = __shfl_sync(tmask, w, lane & ~3);
+      if ((int64_t)w >= total) {
+        exhausted = true;
+        break;
+      }
+      pid = (int64_t)w;
+      const int64_t t = pid / A.restarts;
+      bool skip = A.active && A.active[t] == 0;
+      if (!skip && A.early_exit) skip = *((volatile int32_t*)(A.solved + t)) != 0;
+      if (skip) {
+        if (sub == 0) {
+          A.out_loss[pid] = DBL_MAX;
+          A.out_iters[pid] = 0;
+        }
+        for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = 0.0;
+        continue;
+      }
+      // initial point into the trial buffer (buffer cur^1), target columns into registers
+      cur = 0;
+      double* xt = base + 2 * P;
+      for (int j = sub; j < P; j += LPP)
+        xt[j] = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double2 v = *reinterpret_cast<const double2*>(A.V + t * 32 + (a * 4 + sub) * 2);
+        vcol[0][a] = mkc(v.x, v.y);
+      }
+      state = ST_INIT;
+      iter = 0;
+      ls = 0;
+      hcount = 0;
+      hpos = 0;
+      gamma = 1.0;
+      slow = false;
+    }
+    if (__all_sync(0xffffffffu, state == ST_IDLE)) break;
+    __syncwarp();
+
+    // ---------------- one loss+grad evaluation per team (convergent) -----------------------------
+    double* xt = base + 2 * (cur ^ 1) * P;
+    double* gt = xt + P;
+    const double ft = loss_grad_team<LPP, GM, true>(kt, xt, tg, gt, vcol, A.cost_kind, sub, nullptr);
+    if (state == ST_IDLE) continue;
+    ++evals;
+
+    // ---------------- per-team bookkeeping (divergent across teams) ------------------------------
+    double* x = base + 2 * cur * P;
+    double* g = x + P;
+    bool accepted = false;
+    if (state == ST_INIT) {
+      accepted = true;
+    } else if (ft <= f + kArmijo * alpha * gd) {  // Armijo; NaN compares false
+      accepted = true;
+      // history pair: s = xt - x, y = gt - g
+      double* s = S + hpos * P;
+      double* y = Y + hpos * P;
+      double sy = 0.0, yy = 0.0;
+      for (int j = sub; j < P; j += LPP) {
+        const double sj = xt[j] - x[j], yj = gt[j] - g[j];
+        s[j] = sj;
+        y[j] = yj;
+        sy = fma(sj, yj, sy);
+        yy = fma(yj, yj, yy);
+      }
+      sy = tsum(sy, tmask);
+      yy = tsum(yy, tmask);
+      if (sy > 1e-14 * yy && yy > 0.0) {  // cautious update: keep only positive-curvature pairs
+        if (sub == 0) rho[hpos] = 1.0 / sy;
+        gamma = sy / yy;
+        hpos = (hpos + 1 == m) ? 0 : hpos + 1;
+        hcount = min(hcount + 1, m);
+      }
+      ++iter;
+    }
+    bool done = false;
+    if (accepted) {
+      cur ^= 1;  // trial point becomes the current point
+      x = xt;
+      g = gt;
+      f = ft;
+      double gmax = 0.0;
+      for (int j = sub; j < P; j += LPP) gmax = fmax(gmax, fabs(g[j]));
+      gmax = tmax(gmax, tmask);
+      // progress checkpoint every 32 accepted steps: "slow" = less than 4x reduction since the last one
+      if ((iter & 31) == 0) {
+        slow = iter > 0 && f > 0.25 * f_chk;
+        f_chk = f;
+      }
+      // gtol_far is scipy's BFGS default gtol (1e-5), where the reference stops unconditionally.  Here it only
+      // ends restarts that sit at a non-zero local minimum (f > f_far) or have stopped making real progress;
+      // restarts still converging towards zero loss run on to f_stop / gtol.
+      done = (f < A.f_stop) || (gmax < A.gtol) || (gmax < A.gtol_far && (f > A.f_far || slow)) ||
+             (iter >= A.max_iter) || !(f == f);
+      if (!done && A.early_exit) done = *((volatile int32_t*)(A.solved + pid / A.restarts)) != 0;
+      if (!done) {
+        __syncwarp(tmask);
+        // two-loop recursion: D <- -H g
+        for (int j = sub; j < P; j += LPP) D[j] = g[j];
+        __syncwarp(tmask);
+        for (int h = 0; h < hcount; ++h) {
+          int slot = hpos - 1 - h;
+          if (slot < 0) slot += m;
+          const double* s = S + slot * P;
+          const double* y = Y + slot * P;
+          double a = 0.0;
+          for (int j = sub; j < P; j += LPP) a = fma(s[j], D[j], a);
+          a = tsum(a, tmask) * rho[slot];
+          if (sub == 0) alp[slot] = a;
+          for (int j = sub; j < P; j += LPP) D[j] = fma(-a, y[j], D[j]);
+        }
+        __syncwarp(tmask);
+        for (int j = sub; j < P; j += LPP) D[j] *= gamma;
+        for (int h = hcount - 1; h >= 0; --h) {
+          int slot = hpos - 1 - h;
+          if (slot < 0) slot += m;
+          const double* s = S + slot * P;
+          const double* y = Y + slot * P;
+          double b = 0.0;
+          for (int j = sub; j < P; j += LPP) b = fma(y[j], D[j], b);
+          b = tsum(b, tmask) * rho[slot];
+          const double c = alp[slot] - b;
+          for (int j = sub; j < P; j += LPP) D[j] = fma(c, s[j], D[j]);
+        }
+        double gdn = 0.0, gg = 0.0;
+        for (int j = sub; j < P; j += LPP) {
+          const double dj = -D[j];
+          D[j] = dj;
+          gdn = fma(g[j], dj, gdn);
+          gg = fma(g[j], g[j], gg);
+        }
+        gdn = tsum(gdn, tmask);
+        gg = tsum(gg, tmask);
+        if (hcount == 0 || !(gdn < 0.0)) {  // first step or not a descent direction: steepest descent, unit length
+          hcount = 0;
+          for (int j = sub; j < P; j += LPP) D[j] = -g[j];
+          gdn = -gg;
+          alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+        } else {
+          alpha = 1.0;
+        }
+        gd = gdn;
+        ls = 0;
+        state = ST_LS;
+      }
+    } else {
+      // backtrack with the cubic through (0, f, gd) and (alpha, ft, gdt), safeguarded to [0.1, 0.5] alpha
+      double gdt = 0.0;
+      for (int j = sub; j < P; j += LPP) gdt = fma(gt[j], D[j], gdt);
+      gdt = tsum(gdt, tmask);
+      double an = 0.5 * alpha;
+      if (ft == ft && gdt == gdt) {
+        const double d1 = gd + gdt - 3.0 * (ft - f) / alpha;
+        const double disc = d1 * d1 - gd * gdt;
+        if (disc >= 0.0) {
+          const double d2 = sqrt(disc);
+          const double den = gdt - gd + 2.0 * d2;
+          if (den != 0.0) {
+            const double cand = alpha - alpha * (gdt + d2 - d1) / den;
+            if (cand == cand) an = cand;
+          }
+        }
+      }
+      alpha = fmin(fmax(an, 0.1 * alpha), 0.5 * alpha);
+      ++ls;
+      if (ls > 30) {
+        if (hcount > 0) {  // curvature model is bad: restart from steepest descent
+          hcount = 0;
+          double gg = 0.0;
+          for (int j = sub; j < P; j += LPP) {
+            D[j] = -g[j];
+            gg = fma(g[j], g[j], gg);
+          }
+          gg = tsum(gg, tmask);
+          gd = -gg;
+          alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+          ls = 0;
+        } else {
+          done = true;  // no progress possible at working precision
+        }
+      }
+    }
+    if (done) {
+      if (sub == 0) {
+        A.out_loss[pid] = f;
+        A.out_iters[pid] = iter;
+        if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + pid / A.restarts, 1);
+      }
+      for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = x[j];
+      state = ST_IDLE;
+    } else {
+      __syncwarp(tmask);
+      double* xn = base + 2 * (cur ^ 1) * P;
+      for (int j = sub; j < P; j += LPP) xn[j] = fma(alpha, D[j], x[j]);
+    }
+  }
+  if (A.out_evals && sub == 0 && evals) atomicAdd(A.out_evals, evals);
+}
+
+static int team_doubles(const KTemplate& kt, int m) {
+  int rs = (5 + 2 * m) * kt.P + 2 * m + ((5 * kt.P) & 1) + 2 * kt.n_trig;
+  while ((rs & 15) != 4) ++rs;  // 4 (mod 16): the 4 teams of a half-warp hit disjoint bank groups
+  return rs;
+}
+
+}  // namespace slam
+
+using namespace slam;
+
+extern "C" void slam_opt_defaults(SlamOptOpts* o) {
+  if (!o) return;
+  o->max_iter = 2500;            // optimizer.py:274 options={"maxiter": 2500}
+  o->history = 0;
+  o->cost_kind = SLAM_COST_BASIC;
+  o->early_exit = 1;
+  o->success_threshold = 1e-10;  // optimizer.py:18
+  o->f_stop = 1e-13;
+  o->gtol = 1e-9;
+  o->gtol_far = 1e-5;            // scipy BFGS default gtol, applied to restarts stuck at a non-zero local minimum
+  o->f_far = 1e-6;
+  o->x0_lo = 0.0;                // basis.py:111: np.random.random(P) * 2 pi
+  o->x0_hi = 6.283185307179586;
+}
+
+extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
+                                const double* x0, int64_t ldx0, uint64_t seed, const int32_t* active,
+                                const SlamOptOpts* opts, double* out_loss, double* out_x, int32_t* out_iters,
+                                unsigned long long* out_evals, void* stream) {
+  if (!desc || !V || !opts || !out_loss || !out_x || !out_iters || Nt < 0 || restarts < 1) return SLAM_ERR_INVALID;
+  if (x0 && ldx0 < desc->n_params) return SLAM_ERR_INVALID;
+  if (opts->cost_kind != SLAM_COST_BASIC && opts->cost_kind != SLAM_COST_SQUARE) return SLAM_ERR_UNSUPPORTED;
+  if (opts->max_iter < 1 || opts->history < 0 || opts->history > 8) return SLAM_ERR_INVALID;
+  if (desc->n_params < 1) return SLAM_ERR_INVALID;
+  if (Nt == 0) return SLAM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  KTemplate kt;
+  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/false);
+  if (rc != SLAM_OK) return rc;
+  if (kt.gmode == GM_DENSE && desc->gate_kind != SLAM_GATE_FIXED) {
+    rc = lower_const_smush(desc, &kt, st);
+    if (rc != SLAM_OK) return rc;
+  }
+  int dev = 0, sms = 0, max_smem = 0;
+  SLAM_CUDA_CHECK(cudaGetDevice(&dev));
+  SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // history length and teams per CTA from the shared-memory budget (one persistent CTA per SM)
+  int m = opts->history ? opts->history : 6;
+  int teams = 64;
+  if (!opts->history)
+    while (m > 4 && (size_t)team_doubles(kt, m) * 8 * 64 > (size_t)max_smem) --m;
+  while (teams > 8 && (size_t)team_doubles(kt, m) * 8 * teams > (size_t)max_smem) teams -= 8;
+  const int RS = team_doubles(kt, m);
+  const size_t smem = (size_t)RS * 8 * teams;
+  if (smem > (size_t)max_smem) return SLAM_ERR_UNSUPPORTED;
+
+  unsigned long long* next = nullptr;
+  int32_t* solved = nullptr;
+  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&next, sizeof(unsigned long long), st));
+  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&solved, sizeof(int32_t) * (size_t)Nt, st));
+  SLAM_CUDA_CHECK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
+  SLAM_CUDA_CHECK(cudaMemsetAsync(solved, 0, sizeof(int32_t) * (size_t)Nt, st));
+
+  LbfgsArgs A;
+  A.V = V; A.x0 = x0; A.ldx0 = ldx0; A.seed = seed; A.active = active; A.Nt = Nt; A.restarts = restarts;
+  A.m = m; A.RS = RS; A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit;
+  A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
+  A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
+  A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
+  A.next = next; A.solved = solved;
+
+  const int64_t total = Nt * (int64_t)restarts;
+  int grid = (int)std::min<int64_t>((int64_t)sms, (total + teams - 1) / teams);
+  const int threads = teams * LPP;
+#define SLAM_LAUNCH_LBFGS(GMV)                                                                                    \
+  do {                                                                                                            \
+    auto kern = lbfgs_kernel<GMV>;                                                                                \
+    SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    kern<<<grid, threads, smem, st>>>(kt, A);                                                                     \
+  } while (0)
+  switch (kt.gmode) {
+    case GM_SYM: SLAM_LAUNCH_LBFGS(GM_SYM); break;
+    case GM_BLOCK: SLAM_LAUNCH_LBFGS(GM_BLOCK); break;
+    case GM_DENSE: SLAM_LAUNCH_LBFGS(GM_DENSE); break;
+    default: cudaFreeAsync(next, st); cudaFreeAsync(solved, st); return SLAM_ERR_UNSUPPORTED;
+  }
+#undef SLAM_LAUNCH_LBFGS
+  SLAM_CUDA_CHECK(cudaGetLastError());
+  SLAM_CUDA_CHECK(cudaFreeAsync(next, st));
+  SLAM_CUDA_CHECK(cudaFreeAsync(solved, st));
+  return SLAM_OK;
+}

@@ -6,10 +6,6 @@ int lower_const_smush(const SlamTemplateDesc*, KTemplate*, cudaStream_t) { retur
 }
 // temporary stubs (replaced as the kernels land)
 extern "C" {
-int slam_weyl(const double*, int64_t, double*, double*, int32_t, void*) { return SLAM_ERR_UNSUPPORTED; }
-void slam_opt_defaults(SlamOptOpts*) {}
-int slam_lbfgs_solve(const SlamTemplateDesc*, const double*, int64_t, int32_t, const double*, int64_t, uint64_t, const int32_t*,
-                     const SlamOptOpts*, double*, double*, int32_t*, unsigned long long*, void*) { return SLAM_ERR_UNSUPPORTED; }
 int slam_coverage_mc(const SlamTemplateDesc*, uint64_t, int64_t, int64_t, double, double, int32_t, unsigned long long*, double*, void*) { return SLAM_ERR_UNSUPPORTED; }
 int slam_pd_trajectory(const double*, const double*, const double*, int32_t, int32_t, double, int32_t, double*, double*, int64_t, void*) { return SLAM_ERR_UNSUPPORTED; }
 }

@@ -1,0 +1,49 @@
+// slam_weyl.cu -- K3 batch kernel: one 4x4 unitary per thread.
+#include "slam_host.h"
+#include "slam_weyl.cuh"
+
+namespace slam {
+
+__global__ void __launch_bounds__(128) weyl_kernel(const double* __restrict__ U, int64_t B, double* __restrict__ c,
+                                                   double* __restrict__ g, int flags) {
+  // stage the CTA's 128 matrices through shared memory: global reads are fully coalesced and each thread
+  // then reads its own matrix with a conflict-free stride (33 doubles)
+  __shared__ double sm[128 * 33];
+  const int tid = threadIdx.x;
+  const int64_t first = (int64_t)blockIdx.x * 128;
+  const int nrows = (int)min((int64_t)128, B - first);
+  const double* src = U + first * 32;
+  for (int e = tid; e < nrows * 32; e += 128) sm[(e >> 5) * 33 + (e & 31)] = src[e];
+  __syncthreads();
+  if (tid >= nrows) return;
+  cd M[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) M[i][j] = mkc(sm[tid * 33 + 2 * (4 * i + j)], sm[tid * 33 + 2 * (4 * i + j) + 1]);
+  double cc[3], gg[3];
+  weyl_makhlin(M, flags, c ? cc : nullptr, g ? gg : nullptr);
+  const int64_t b = first + tid;
+  if (c) {
+    c[3 * b] = cc[0];
+    c[3 * b + 1] = cc[1];
+    c[3 * b + 2] = cc[2];
+  }
+  if (g) {
+    g[3 * b] = gg[0];
+    g[3 * b + 1] = gg[1];
+    g[3 * b + 2] = gg[2];
+  }
+}
+
+}  // namespace slam
+
+extern "C" int slam_weyl(const double* U, int64_t B, double* c, double* g, int32_t flags, void* stream) {
+  using namespace slam;
+  if (!U || B < 0 || (!c && !g)) return SLAM_ERR_INVALID;
+  if (B == 0) return SLAM_OK;
+  const unsigned grid = (unsigned)((B + 127) / 128);
+  weyl_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(U, B, c, g, flags);
+  SLAM_CUDA_CHECK(cudaGetLastError());
+  return SLAM_OK;
+}

@@ -1,0 +1,105 @@
+"""K3 parity: Weyl-chamber coordinates and Makhlin invariants vs the oracle (weylchamber algorithm)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from slam_decomposition_b200 import engine
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10  # north_star: Weyl coordinates within 1e-10 absolute
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kats.json")))
+
+
+def _dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.complex128), device="cuda")
+
+
+def _coords(U, **kw):
+    c, g = engine.weyl(_dev(U), want_g=True, **kw)
+    return c.cpu().numpy(), g.cpu().numpy()
+
+
+def test_golden_gates_rounded():
+    named = {
+        "CX": O.CNOT, "SWAP": O.SWAP, "I": np.eye(4), "iSWAP": O.ISWAP, "sqrt_iSWAP": O.riswap(0.5),
+        "B": O.berkeley(), "FSIM": O.fsim(KATS["B5"]["fsim_theta"], KATS["B5"]["fsim_phi"]),
+    }
+    U = np.stack(list(named.values()))
+    c, g = _coords(U, round8=True)
+    for i, (name, M) in enumerate(named.items()):
+        assert tuple(c[i]) == O.c1c2c3(M), name
+        assert tuple(g[i]) == O.g1g2g3(M), name
+    assert tuple(c[0]) == tuple(KATS["B4"]["CX"]) and tuple(c[1]) == tuple(KATS["B4"]["SWAP"])
+    assert tuple(c[6]) == tuple(KATS["B5"]["c1c2c3"])
+    for name in ("I", "iSWAP", "sqrt_iSWAP"):
+        i = list(named).index(name)
+        assert tuple(g[i]) == tuple(KATS["B10"][name])
+
+
+def test_basis_gates_b3():
+    for name, gd in KATS["B3"]["gates"].items():
+        G = O.conversion_gain(0, 0, gd["gc"], gd["gg"], gd["t"])
+        c, _ = _coords(G[None], fold=True, round8=True)
+        assert np.allclose(c[0], gd["c1c2c3_folded"], atol=1e-8), name
+
+
+def test_haar_batch_unrounded():
+    rng = np.random.default_rng(0)
+    U = O.haar_unitary(rng, 5000)
+    c, g = _coords(U)
+    co = O.c1c2c3_raw(U)
+    go = O.g1g2g3_raw(U)
+    # compare folded coordinates (raw c1 mirrors when c3 crosses 0: SURVEY hard parts)
+    d = np.abs(O.fold_c1(c) - O.fold_c1(co)).max(axis=1)
+    assert np.sum(d > TOL) == 0, d.max()
+    assert np.abs(g - go).max() < TOL
+    cf, _ = _coords(U, fold=True)
+    assert np.abs(cf - O.fold_c1(co)).max() < TOL
+
+
+def test_degenerate_and_locally_equivalent_inputs():
+    """Degenerate spectra (CNOT/iSWAP/SWAP/identity classes) dressed with random local gates."""
+    rng = np.random.default_rng(1)
+    base = [np.eye(4), O.CNOT, O.SWAP, O.ISWAP, O.riswap(0.5), O.berkeley(), O.conversion_gain(0, 0, np.pi / 4, np.pi / 4, 0.5)]
+    Us, ref = [], []
+    for M in base:
+        cm = O.fold_c1(O.c1c2c3_raw(M))
+        for _ in range(50):
+            k1 = np.kron(O.u3(*rng.uniform(0, 7, 3)), O.u3(*rng.uniform(0, 7, 3)))
+            k2 = np.kron(O.u3(*rng.uniform(0, 7, 3)), O.u3(*rng.uniform(0, 7, 3)))
+            Us.append(np.exp(1j * rng.uniform(0, 7)) * (k1 @ M @ k2))
+            ref.append(cm)
+    c, g = _coords(np.stack(Us), fold=True)
+    ref = np.array(ref)
+    # on chamber faces the representative (c1 vs 1-c1 is folded; c3=0 plane) is unique after folding
+    assert np.abs(c - ref).max() < 1e-7  # degenerate points: sqrt-type sensitivity of the *reference* itself
+    go = O.g1g2g3_raw(np.stack(Us))
+    assert np.abs(g - go).max() < TOL
+
+
+def test_template_outputs_b1_b2():
+    from helpers import make_pair
+
+    desc, orc = make_pair("riswap", (0.5,), k=3)
+    vals = {}
+    p = 0
+    for tri in KATS["B1"]["u3_triples"]:
+        for v in tri:
+            vals[f"P{p}"] = v
+            p += 1
+    x = torch.as_tensor(np.array([[vals[n] for n in orc.names_sorted]]), device="cuda")
+    U = engine.template_eval(desc, x)
+    c, _ = engine.weyl(U, round8=True)
+    assert tuple(c[0].tolist()) == tuple(KATS["B1"]["c1c2c3"])
+
+
+def test_ragged_sizes():
+    rng = np.random.default_rng(2)
+    for B in (1, 127, 128, 129, 1000):
+        U = O.haar_unitary(rng, B)
+        c, _ = _coords(U, fold=True)
+        assert np.abs(c - O.fold_c1(O.c1c2c3_raw(U))).max() < TOL
