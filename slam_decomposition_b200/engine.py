@@ -19,6 +19,17 @@ __all__ = [
 ]
 
 
+# number of kernel launches issued through this module (bench.py reports it as `gpu_launches`)
+LAUNCHES = 0
+# when set to a list, lbfgs_solve appends (k, start_event, end_event) for per-launch device timing
+LBFGS_EVENTS = None
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def require_cuda() -> torch.device:
     if not torch.cuda.is_available():
         raise _lib.SlamError("slam_decomposition_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -59,6 +70,7 @@ def template_eval(desc: SlamTemplateDesc, x: torch.Tensor) -> torch.Tensor:
         lib = _enter(x)
         check(lib.slam_template_eval(C.byref(desc), _ptr(x), max(x.stride(0), desc.n_params), _ptr(U), B, _stream()),
               "slam_template_eval")
+    _count()
     return U
 
 
@@ -86,6 +98,7 @@ def loss_grad(desc: SlamTemplateDesc, x: torch.Tensor, V: torch.Tensor, tgt_idx:
         lib = _enter(x)
         check(lib.slam_loss_grad(C.byref(desc), _ptr(x), max(x.stride(0), P), _ptr(V), V.shape[0], _ptr(tgt_idx),
                                  int(cost_kind), _ptr(loss), _ptr(grad), P, _ptr(trace), B, _stream()), "slam_loss_grad")
+    _count()
     return loss, grad, trace
 
 
@@ -101,6 +114,7 @@ def weyl(U: torch.Tensor, fold: bool = False, round8: bool = False, want_c: bool
     with torch.cuda.device(U.device):
         lib = _enter(U)
         check(lib.slam_weyl(_ptr(U), B, _ptr(c), _ptr(g), flags, _stream()), "slam_weyl")
+    _count()
     return c, g
 
 
@@ -112,8 +126,8 @@ def opt_defaults() -> SlamOptOpts:
 
 def lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: SlamOptOpts,
                 x0: Optional[torch.Tensor] = None, seed: int = 0, active: Optional[torch.Tensor] = None,
-                evals: Optional[torch.Tensor] = None):
-    """K5: returns (loss [Nt,R], x [Nt,R,P], iters [Nt,R])."""
+                evals: Optional[torch.Tensor] = None, out: Optional[tuple] = None):
+    """K5: returns (loss [Nt,R], x [Nt,R,P], iters [Nt,R]).  `out` = preallocated (loss, x, iters) to reuse."""
     V = _dev(V, torch.complex128, "V")
     Nt = V.shape[0]
     P = desc.n_params
@@ -124,14 +138,29 @@ def lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: Sl
             raise ValueError(f"x0 must be [{Nt},{restarts},{P}]")
     if active is not None:
         active = _dev(active, torch.int32, "active")
-    loss = torch.empty((Nt, restarts), dtype=torch.float64, device=V.device)
-    x = torch.empty((Nt, restarts, P), dtype=torch.float64, device=V.device)
-    iters = torch.empty((Nt, restarts), dtype=torch.int32, device=V.device)
+    if out is not None:
+        loss, x, iters = out
+        if (loss.shape != (Nt, restarts) or x.shape != (Nt, restarts, P) or iters.shape != (Nt, restarts)
+                or not (loss.is_contiguous() and x.is_contiguous() and iters.is_contiguous())):
+            raise ValueError("lbfgs_solve: preallocated outputs have the wrong shape")
+        _dev(loss, torch.float64, "out loss"), _dev(x, torch.float64, "out x"), _dev(iters, torch.int32, "out iters")
+    else:
+        loss = torch.empty((Nt, restarts), dtype=torch.float64, device=V.device)
+        x = torch.empty((Nt, restarts, P), dtype=torch.float64, device=V.device)
+        iters = torch.empty((Nt, restarts), dtype=torch.int32, device=V.device)
     with torch.cuda.device(V.device):
         lib = _enter(V)
+        ev = None
+        if LBFGS_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         check(lib.slam_lbfgs_solve(C.byref(desc), _ptr(V), Nt, int(restarts), _ptr(x0), ld, C.c_uint64(seed), _ptr(active),
                                    C.byref(opts), _ptr(loss), _ptr(x), _ptr(iters), _ptr(evals), _stream()),
               "slam_lbfgs_solve")
+        if ev is not None:
+            ev[1].record()
+            LBFGS_EVENTS.append((desc.k, ev[0], ev[1]))
+    _count()
     return loss, x, iters
 
 
@@ -149,6 +178,7 @@ def coverage_mc(desc: SlamTemplateDesc, seed: int, first_sample: int, n_samples:
         lib = _enter(hist)
         check(lib.slam_coverage_mc(C.byref(desc), C.c_uint64(seed), int(first_sample), int(n_samples), float(lo), float(hi),
                                    int(nbins), _ptr(hist), _ptr(coords), _stream()), "slam_coverage_mc")
+    _count()
     return hist, coords
 
 
@@ -168,6 +198,7 @@ def pd_trajectory(gate: torch.Tensor, gx: torch.Tensor, gy: torch.Tensor, dt: fl
         lib = _enter(gx)
         check(lib.slam_pd_trajectory(_ptr(gate), _ptr(gx), _ptr(gy), N, R, float(dt), flags, _ptr(coords), _ptr(Uf), B,
                                      _stream()), "slam_pd_trajectory")
+    _count()
     return coords, Uf
 
 

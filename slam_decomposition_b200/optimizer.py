@@ -1,0 +1,254 @@
+"""``TemplateOptimizer`` (reference: src/slam/optimizer.py:24-313) over the batched device L-BFGS.
+
+The reference runs, per target: for k in spanning range -> for restart in range(R) ->
+``scipy.optimize.minimize(BFGS, finite-difference gradient)`` with early exits.  Here all targets x
+restarts of one template size k are solved concurrently by ``slam_lbfgs_solve`` (analytic gradients,
+state in shared memory); the k-loop stays on the host and carries a per-target ``active`` mask, which
+reproduces "smallest k that reaches the success threshold" (optimizer.py:233, 297-303).
+
+Return contract kept (optimizer.py:186): ``(training_loss, coordinate_list, [DataDictEntry])``.
+"""
+from __future__ import annotations
+
+import logging
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from .basis import CircuitTemplate, HamiltonianTemplate, _CircuitTemplateBase
+from .basis_abc import DataDictEntry, VariationalTemplate
+from .basisv2 import CircuitTemplateV2
+from .cost_function import UnitaryCostFunction
+from .sampler import SampleFunction
+from .weyl import c1c2c3, c1c2c3_batch
+
+SUCCESS_THRESHOLD = 1e-10
+TRAINING_RESTARTS = 5
+
+
+class TemplateOptimizer:
+    def __init__(self, basis: VariationalTemplate, objective: UnitaryCostFunction, use_callback=False,
+                 override_fail=False, success_threshold=None, training_restarts=None, override_method=None):
+        self.basis = basis
+        self.objective = objective
+        self.preseeding = self.basis.preseeded
+        self.use_callback = use_callback
+        self.training_loss = []
+        self.coordinate_list = []
+        self.best_cycle_list = []
+        self.override_fail = override_fail
+        self.override_method = override_method
+        self.success_threshold = SUCCESS_THRESHOLD if success_threshold is None else success_threshold
+        self.training_restarts = TRAINING_RESTARTS if training_restarts is None else training_restarts
+        assert not (self.preseeding and self.override_fail)
+        assert not (self.preseeding and self.basis.n_qubits != 2)
+        self.last_stats = {}
+        self._ws = None
+        self.launch_evals = []  # (k, loss+grad evaluations) per slam_lbfgs_solve launch while engine.LBFGS_EVENTS is on
+
+    # ------------------------------------------------------------------------------------------
+    # reference entry points
+    # ------------------------------------------------------------------------------------------
+    def approximate_target_U(self, target_U):
+        """Atomic training function for one target (optimizer.py:65-119)."""
+        V = torch.as_tensor(np.asarray(target_U, dtype=np.complex128)[None], device=engine.require_cuda())
+        return self._approximate_batch(V)[0]
+
+    def approximate_from_distribution(self, sampler: SampleFunction):
+        """All targets of the sampler at once (optimizer.py:180-186 runs them one by one)."""
+        if hasattr(sampler, "batch"):
+            V = sampler.batch(engine.require_cuda())
+        else:
+            V = torch.as_tensor(np.stack([np.asarray(u, dtype=np.complex128) for u in sampler]),
+                                device=engine.require_cuda())
+        target_data = self._approximate_batch(V)
+        return self.training_loss, self.coordinate_list, target_data
+
+    def _run(self, target_u, target_spanning_range):
+        """(best_result, best_Xk, best_cycles) for one target (optimizer.py:188-313)."""
+        V = torch.as_tensor(np.asarray(target_u, dtype=np.complex128)[None], device=engine.require_cuda())
+        res = self._run_batch(V, target_spanning_range)
+        P = int(res["best_P"][0])
+        return float(res["best_loss"][0]), res["best_x"][0, :P].cpu().numpy(), int(res["best_k"][0])
+
+    # ------------------------------------------------------------------------------------------
+    # batched core
+    # ------------------------------------------------------------------------------------------
+    def _cost_kind(self) -> int:
+        if not isinstance(self.objective, UnitaryCostFunction):
+            raise ValueError("Unrecognized Cost Function")  # optimizer.py:211
+        ck = self.objective.cost_kind
+        if ck not in (_lib.COST_BASIC, _lib.COST_SQUARE):
+            raise NotImplementedError(
+                f"{type(self.objective).__name__}: the device L-BFGS fuses BasicCost / SquareCost; "
+                "other functionals are available through unitary_fidelity() only")
+        return ck
+
+    def _x0(self, Nt: int, device) -> tuple:
+        """(x0 tensor | None, lo, hi): initial points.  Uniform-box templates use the kernel's Philox stream."""
+        b = self.basis
+        if isinstance(b, CircuitTemplateV2):
+            lo, hi = b.x0_bound_arrays()
+            if np.all(lo == lo[0]) and np.all(hi == hi[0]):
+                return None, float(lo[0]), float(hi[0])
+            gen = torch.Generator(device=device).manual_seed(int(np.random.randint(0, 2 ** 31 - 1)))
+            u = torch.rand((Nt, self.training_restarts, lo.size), dtype=torch.float64, device=device, generator=gen)
+            lo_t, hi_t = torch.as_tensor(lo, device=device), torch.as_tensor(hi, device=device)
+            return lo_t + (hi_t - lo_t) * u, 0.0, 1.0
+        return None, 0.0, 2 * np.pi  # CircuitTemplate: np.random.random(P) * 2 pi (basis.py:111)
+
+    def _run_batch(self, V: torch.Tensor, k_range: Sequence[int], opts: Optional[_lib.SlamOptOpts] = None,
+                   keep_history: bool = False) -> dict:
+        b = self.basis
+        if not isinstance(b, _CircuitTemplateBase):
+            raise NotImplementedError("the device optimizer runs CircuitTemplate / CircuitTemplateV2")
+        if getattr(b, "using_bounds", False) or getattr(b, "using_constraints", False):
+            raise NotImplementedError("bounded / constrained templates (L-BFGS-B / SLSQP selection, optimizer.py:255-268)")
+        if self.override_method not in (None, "BFGS", "L-BFGS-B"):
+            raise NotImplementedError(f"override_method={self.override_method}")
+        ck = self._cost_kind()
+        device = V.device
+        Nt = V.shape[0]
+        R = int(self.training_restarts)
+        if opts is None:
+            opts = engine.opt_defaults()
+        opts.cost_kind = ck
+        opts.success_threshold = float(self.success_threshold)
+        opts.f_stop = min(opts.f_stop, 1e-3 * float(self.success_threshold))
+        # persistent workspace: output tables are reused across k and across calls (no allocator churn per sweep)
+        ws = self._ws
+        if ws is None or ws["key"] != (Nt, R, str(device)):
+            ws = {"key": (Nt, R, str(device)), "xcap": 0, "xbuf": None,
+                  "loss": torch.empty((Nt, R), dtype=torch.float64, device=device),
+                  "iters": torch.empty((Nt, R), dtype=torch.int32, device=device),
+                  "ar": torch.arange(Nt, device=device)}
+            self._ws = ws
+        best_loss = torch.full((Nt,), float("inf"), dtype=torch.float64, device=device)
+        best_k = torch.full((Nt,), -1, dtype=torch.int32, device=device)
+        best_P = torch.zeros((Nt,), dtype=torch.int32, device=device)
+        best_x = None
+        active = torch.ones((Nt,), dtype=torch.int32, device=device)
+        evals = torch.zeros(1, dtype=torch.int64, device=device)
+        per_k = []
+        ar = ws["ar"]
+        timing = engine.LBFGS_EVENTS is not None
+        for k in k_range:
+            logging.info(f"Starting opt on template size {k}")
+            b.build(n_repetitions=k)
+            desc = b.desc
+            P = desc.n_params
+            if P > ws["xcap"]:
+                ws["xbuf"] = None
+                ws["xbuf"] = torch.empty(Nt * R * P, dtype=torch.float64, device=device)
+                ws["xcap"] = P
+            x = ws["xbuf"][: Nt * R * P].view(Nt, R, P)
+            x0, lo, hi = self._x0(Nt, device)
+            opts.x0_lo, opts.x0_hi = lo, hi
+            seed = int(np.random.randint(0, 2 ** 62))
+            ev_before = int(evals.item()) if timing else 0
+            loss, x, iters = engine.lbfgs_solve(desc, V, R, opts, x0=x0, seed=seed, active=active, evals=evals,
+                                                out=(ws["loss"], x, ws["iters"]))
+            if timing:
+                self.launch_evals.append((k, int(evals.item()) - ev_before))
+            lmin, rmin = loss.min(dim=1)
+            improved = (active != 0) & (lmin < best_loss)
+            xsel = x[ar, rmin]
+            if best_x is None or best_x.shape[1] < P:
+                nb = torch.zeros((Nt, P), dtype=torch.float64, device=device)
+                if best_x is not None:
+                    nb[:, : best_x.shape[1]] = best_x
+                best_x = nb
+            best_x[:, :P] = torch.where(improved[:, None], xsel, best_x[:, :P])
+            if best_x.shape[1] > P:
+                best_x[:, P:] = torch.where(improved[:, None], torch.zeros_like(best_x[:, P:]), best_x[:, P:])
+            best_loss = torch.where(improved, lmin, best_loss)
+            best_k = torch.where(improved, torch.full_like(best_k, k), best_k)
+            best_P = torch.where(improved, torch.full_like(best_P, P), best_P)
+            if keep_history:  # per-restart tables are only copied out when the caller wants histories
+                per_k.append({"k": k, "loss": loss.clone(), "x": x.clone(), "iters": iters.clone(),
+                              "active": active.clone(), "desc": desc})
+            active = ((active != 0) & ~(best_loss < self.success_threshold)).to(torch.int32)
+            n_left = int(active.sum().item())
+            logging.info(f"Cycle (k ={k}), solved {Nt - n_left}/{Nt}")
+            if n_left == 0:
+                logging.info(f"Break on cycle {k}")
+                break
+        self.last_stats = {"evals": int(evals.item())}
+        return {"best_loss": best_loss.cpu().numpy(), "best_k": best_k.cpu().numpy(), "best_P": best_P.cpu().numpy(),
+                "best_x": best_x, "per_k": per_k}
+
+    def approximate_targets(self, targets, k_range: Optional[Sequence[int]] = None, opts=None) -> dict:
+        """Host-buffer batch API: ``targets`` complex128 [Nt,4,4] (numpy, or a pinned/CPU torch tensor) ->
+        dict of numpy arrays ``loss [Nt]``, ``cycles [Nt]``, ``success [Nt]``, ``Xk [Nt,Pmax]``, ``n_params [Nt]``.
+        Host->device and device->host copies happen inside this call (this is what bench.py's `e2e` times)."""
+        dev = engine.require_cuda()
+        if isinstance(targets, torch.Tensor):
+            V = targets.to(dev, non_blocking=True)
+        else:
+            V = torch.as_tensor(np.ascontiguousarray(targets, dtype=np.complex128)).to(dev, non_blocking=True)
+        if k_range is None:
+            k_range = self.basis.get_spanning_range(None)
+        res = self._run_batch(V, k_range, opts)
+        return {"loss": res["best_loss"], "cycles": res["best_k"], "n_params": res["best_P"],
+                "success": (res["best_loss"] <= self.success_threshold).astype(np.int32),
+                "Xk": res["best_x"].cpu().numpy()}
+
+    def _approximate_batch(self, V: torch.Tensor) -> List[DataDictEntry]:
+        b = self.basis
+        Nt = V.shape[0]
+        target_coords = c1c2c3_batch(V, round8=True).cpu().numpy() if b.n_qubits == 2 else None
+        b.assign_seed(None)
+        span = b.get_spanning_range(None)
+        res = self._run_batch(V, span, keep_history=self.use_callback)
+        best_x_host = res["best_x"].cpu().numpy()
+        out: List[DataDictEntry] = []
+        failures = []
+        for i in range(Nt):
+            logging.info(f"Starting sample iter {i}")
+            tc = tuple(target_coords[i]) if target_coords is not None else None
+            logging.info(f"Begin search: {tc}")
+            best_result = float(res["best_loss"][i])
+            best_cycles = int(res["best_k"][i])
+            best_Xk = best_x_host[i, : int(res["best_P"][i])].copy()
+            logging.info(f"Overall Best Loss={best_result}")
+            success = best_result <= self.success_threshold
+            if success:
+                logging.info(f"Success: {tc}")
+            else:
+                failures.append(i)
+                logging.info(f"Fail: {tc}")
+            # history lists in the reference's flag format [-1, k, l0, l1, ...] (optimizer.py:238; visualize.py:90-117);
+            # entries are the final loss of every restart of every k tried for this target
+            if self.use_callback:
+                if success or self.override_fail:
+                    tl: list = []
+                    last = None
+                    for rec in res["per_k"]:
+                        if int(rec["active"][i].item()) == 0:
+                            continue
+                        li = rec["loss"][i]
+                        tl.extend([-1, rec["k"]])
+                        tl.extend(float(v) for v in li.tolist() if v < 1e300)
+                        last = rec
+                    self.training_loss.append(tl)
+                    coords = []
+                    if last is not None:
+                        keep = last["loss"][i] < 1e300
+                        if bool(keep.any()):
+                            U = engine.template_eval(last["desc"], last["x"][i][keep].contiguous())
+                            coords = [tuple(c) for c in c1c2c3_batch(U, round8=True).tolist()]
+                    self.coordinate_list.append(coords)
+            else:
+                self.training_loss.append(best_result)
+            self.best_cycle_list.append(best_cycles)
+            out.append(DataDictEntry(int(success), best_result, best_Xk, best_cycles))
+        if failures and not self.override_fail:
+            raise ValueError(
+                "Failed to converge within error threshold. Try increasing restart attempts or increasing temperature "
+                f"scaling on preseed. (targets {failures[:8]}{'...' if len(failures) > 8 else ''})")
+        # leave the template at the size of the last target's best result, as the reference does on failure
+        if out and out[-1].cycles > 0:
+            b.build(n_repetitions=out[-1].cycles)
+        return out
