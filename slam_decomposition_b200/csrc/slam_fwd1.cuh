@@ -1,0 +1,240 @@
+// slam_fwd1.cuh -- thread-per-problem forward evaluation of a template (all gate modes, incl. K4 smush).
+//
+// Used by the forward-only kernels: smush template evaluation (K1 for GM_SMUSH), the fused coverage
+// Monte-Carlo (K6) and the parallel-drive trajectory (K4b).  One thread owns the whole 4x4 running product.
+//
+// K4: a smush gate is the ordered product over T time slices of exp(-i dt H_s) with
+//   H_s = gx_s (e^{i pa} A + h.c.) + gy_s (e^{i pb} B + h.c.) + gc (e^{i pc} A B^dag + h.c.) + gg (e^{i pg} A B + h.c.)
+//         + gz1 A^dag A + gz2 B^dag B                                   (src/slam/hamiltonian.py:114-182)
+// with qutip's create(2) = |1><0|, A = a (x) I, B = I (x) a.  H_s is a general 4x4 Hermitian matrix (no closed
+// form once the phases are non-zero), so each slice is exponentiated by scaling-and-squaring of a degree-12
+// Taylor polynomial (||dt H / 2^s|| <= 1/4 -> truncation < 3e-18), which replaces qutip's Qobj.expm -> scipy Pade.
+#pragma once
+#include "slam_core.cuh"
+
+namespace slam {
+
+// ---- parameter sources -----------------------------------------------------------------------------
+struct GlobalParams {  // row of a [B, ldx] array
+  const double* row;
+  __device__ __forceinline__ double get(int j) const { return row[j]; }
+};
+
+// ---- Hermitian slice generator -----------------------------------------------------------------------
+struct Herm4 {  // h13 = h02, h23 = h01 ; lower triangle = conjugates
+  double d0, d1, d2, d3;
+  cd h01, h02, h03, h12;
+};
+
+__device__ __forceinline__ void herm_mul(const Herm4& H, const cd v[4], cd o[4]) {
+  o[0] = mkc(H.d0 * v[0].re, H.d0 * v[0].im);
+  cacc(o[0], H.h01, v[1]);
+  cacc(o[0], H.h02, v[2]);
+  cacc(o[0], H.h03, v[3]);
+  o[1] = cmulc(v[0], H.h01);  // conj(h01) v0
+  o[1].re = fma(H.d1, v[1].re, o[1].re);
+  o[1].im = fma(H.d1, v[1].im, o[1].im);
+  cacc(o[1], H.h12, v[2]);
+  cacc(o[1], H.h02, v[3]);
+  o[2] = cmulc(v[0], H.h02);
+  const cd t = cmulc(v[1], H.h12);
+  o[2].re += t.re;
+  o[2].im += t.im;
+  o[2].re = fma(H.d2, v[2].re, o[2].re);
+  o[2].im = fma(H.d2, v[2].im, o[2].im);
+  cacc(o[2], H.h01, v[3]);
+  o[3] = cmulc(v[0], H.h03);
+  const cd t1 = cmulc(v[1], H.h02), t2 = cmulc(v[2], H.h01);
+  o[3].re += t1.re + t2.re;
+  o[3].im += t1.im + t2.im;
+  o[3].re = fma(H.d3, v[3].re, o[3].re);
+  o[3].im = fma(H.d3, v[3].im, o[3].im);
+}
+
+// Y[col][row] = exp(-i dt H).  rho = upper bound of ||dt H||_2.
+__device__ __forceinline__ void herm_expm(const Herm4& H, double dt, double rho, cd Y[4][4]) {
+  int s = 0;
+  if (rho > 0.25) s = min(ilogb(rho * 4.0) + 1, 40);
+  const double theta = ldexp(dt, -s);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Y[c][r] = mkc(c == r ? 1.0 : 0.0, 0.0);
+  // Horner: Y <- I + (-i theta / n) H Y, n = 12..1
+  for (int n = 12; n >= 1; --n) {
+    const double a = theta / (double)n;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      cd o[4];
+      herm_mul(H, Y[c], o);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) Y[c][r] = mkc(fma(a, o[r].im, c == r ? 1.0 : 0.0), -(a * o[r].re));  // -i a o + delta
+    }
+  }
+  for (int q = 0; q < s; ++q) {
+    cd Z[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        cd acc = cmul(Y[0][r], Y[c][0]);
+        cacc(acc, Y[1][r], Y[c][1]);
+        cacc(acc, Y[2][r], Y[c][2]);
+        cacc(acc, Y[3][r], Y[c][3]);
+        Z[c][r] = acc;
+      }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) Y[c][r] = Z[c][r];
+  }
+}
+
+// phases of one smush gate: e^{-i phi} for (a, b, c, g) and the static couplings
+struct SmushGate {
+  cd ea, eb, ec, eg;  // e^{-i phi_a}, e^{-i phi_b}, e^{-i phi_c}, e^{-i phi_g}
+  double gc, gg, gz1, gz2;
+};
+
+__device__ __forceinline__ SmushGate smush_gate(double pa, double pb, double pc, double pg, double gc, double gg,
+                                                double gz1, double gz2) {
+  SmushGate G;
+  double s, c;
+  sincos(pa, &s, &c); G.ea = mkc(c, -s);
+  sincos(pb, &s, &c); G.eb = mkc(c, -s);
+  sincos(pc, &s, &c); G.ec = mkc(c, -s);
+  sincos(pg, &s, &c); G.eg = mkc(c, -s);
+  G.gc = gc; G.gg = gg; G.gz1 = gz1; G.gz2 = gz2;
+  return G;
+}
+
+__device__ __forceinline__ void smush_slice(const SmushGate& G, double gx, double gy, double dt, cd Y[4][4]) {
+  Herm4 H;
+  H.d0 = G.gz1 + G.gz2;  // A^dag A = |0><0| (x) I, B^dag B = I (x) |0><0|  (a = create(2) = |1><0|)
+  H.d1 = G.gz1;
+  H.d2 = G.gz2;
+  H.d3 = 0.0;
+  H.h01 = mkc(gy * G.eb.re, gy * G.eb.im);
+  H.h02 = mkc(gx * G.ea.re, gx * G.ea.im);
+  H.h03 = mkc(G.gg * G.eg.re, G.gg * G.eg.im);
+  H.h12 = mkc(G.gc * G.ec.re, G.gc * G.ec.im);
+  const double rho = fabs(dt) * (fabs(gx) + fabs(gy) + fmax(fabs(G.gc), fabs(G.gg)) + fabs(G.gz1) + fabs(G.gz2));
+  herm_expm(H, dt, rho, Y);
+}
+
+// R <- Y R  (both [col][row])
+__device__ __forceinline__ void left_mul(const cd Y[4][4], cd R[4][4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    cd n[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      cd acc = cmul(Y[0][r], R[c][0]);
+      cacc(acc, Y[1][r], R[c][1]);
+      cacc(acc, Y[2][r], R[c][2]);
+      cacc(acc, Y[3][r], R[c][3]);
+      n[r] = acc;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) R[c][r] = n[r];
+  }
+}
+
+// ---- full forward chain, one thread, R[col][row] ------------------------------------------------------
+template <class PS>
+__device__ __forceinline__ double slot_val(const KTemplate& kt, const PS& ps, int g, int s) {
+  const int p = kt.slot_param[g][s];
+  return p >= 0 ? ps.get(p) : kt.slot_const[g][s];
+}
+
+template <class PS>
+__device__ __forceinline__ void fwd1_layer(const KTemplate& kt, const PS& ps, int i, cd R[4][4]) {
+  if (kt.p1q[i][0] < 0 && kt.p1q[i][3] < 0) return;
+  cd A[4], B[4];
+  double s, c;
+  if (kt.vz_only) {
+    sincos(0.5 * ps.get(kt.p1q[i][0]), &s, &c);
+    build_rz(make_double2(c, s), B);
+    sincos(0.5 * ps.get(kt.p1q[i][3]), &s, &c);
+    build_rz(make_double2(c, s), A);
+  } else {
+    double2 t[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double v = ps.get(kt.p1q[i][q]);
+      sincos((q == 0 || q == 3) ? 0.5 * v : v, &s, &c);
+      t[q] = make_double2(c, s);
+    }
+    build_u3(t[0], t[1], t[2], B);
+    build_u3(t[3], t[4], t[5], A);
+  }
+#pragma unroll
+  for (int col = 0; col < 4; ++col) {
+    apply1q<0, OP_N>(R[col], B);
+    apply1q<1, OP_N>(R[col], A);
+  }
+}
+
+template <class PS>
+__device__ __forceinline__ void fwd1_gate(const KTemplate& kt, const PS& ps, int g, cd R[4][4]) {
+  if (kt.gmode == GM_SYM) {
+#pragma unroll
+    for (int col = 0; col < 4; ++col) sym_apply<OP_N>(R[col], kt.gsym[g][0], kt.gsym[g][1], kt.gsym[g][2], kt.gsym[g][3]);
+  } else if (kt.gmode == GM_BLOCK) {
+    BlockGate bg;
+    if (kt.gate_bound[g]) {
+      double2 q[4] = {make_double2(1, 0), make_double2(1, 0), make_double2(1, 0), make_double2(1, 0)};
+      if (kt.gate_kind == SLAM_GATE_RISWAP) {
+        q[0] = make_double2(-1.0, 0.0);
+        sincos(1.5707963267948966 * slot_val(kt, ps, g, 0), &q[2].y, &q[2].x);
+      } else {
+        const double tt = slot_val(kt, ps, g, 4);
+        sincos(slot_val(kt, ps, g, 0), &q[0].y, &q[0].x);
+        sincos(slot_val(kt, ps, g, 1), &q[1].y, &q[1].x);
+        sincos(slot_val(kt, ps, g, 2) * tt, &q[2].y, &q[2].x);
+        sincos(slot_val(kt, ps, g, 3) * tt, &q[3].y, &q[3].x);
+      }
+      bg = block_from_trig(q[0], q[1], q[2], q[3]);
+    } else {
+      const double* c = kt.gblk[g];
+      bg = block_from_trig(make_double2(c[0], c[1]), make_double2(c[2], c[3]), make_double2(c[4], c[5]),
+                           make_double2(c[6], c[7]));
+    }
+#pragma unroll
+    for (int col = 0; col < 4; ++col) block_apply<OP_N>(R[col], bg);
+  } else if (kt.gmode == GM_DENSE) {
+#pragma unroll
+    for (int col = 0; col < 4; ++col) dense_apply<OP_N>(R[col], kt.dense[g]);
+  } else {  // GM_SMUSH
+    const int T = kt.T;
+    const bool ph1q = kt.gate_kind == SLAM_GATE_SMUSH_1QPHASE;
+    const int o = ph1q ? 8 : 4;  // first gx slot
+    SmushGate G;
+    if (ph1q)
+      G = smush_gate(slot_val(kt, ps, g, 0), slot_val(kt, ps, g, 1), slot_val(kt, ps, g, 2), slot_val(kt, ps, g, 3),
+                     slot_val(kt, ps, g, 4), slot_val(kt, ps, g, 5), slot_val(kt, ps, g, 6), slot_val(kt, ps, g, 7));
+    else
+      G = smush_gate(0.0, 0.0, slot_val(kt, ps, g, 0), slot_val(kt, ps, g, 1), slot_val(kt, ps, g, 2),
+                     slot_val(kt, ps, g, 3), 0.0, 0.0);
+    const double dt = slot_val(kt, ps, g, o + 2 * T) / (double)T;  // timestep = t / N (hamiltonian.py:136-137)
+    for (int it = 0; it < T; ++it) {
+      cd Y[4][4];
+      smush_slice(G, slot_val(kt, ps, g, o + it), slot_val(kt, ps, g, o + T + it), dt, Y);
+      left_mul(Y, R);  // later slices multiply on the left (hamiltonian.py:143)
+    }
+  }
+}
+
+template <class PS>
+__device__ __forceinline__ void fwd1_chain(const KTemplate& kt, const PS& ps, cd R[4][4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) R[c][r] = mkc(c == r ? 1.0 : 0.0, 0.0);
+  for (int i = 0; i <= kt.k; ++i) {
+    fwd1_layer(kt, ps, i, R);
+    if (i < kt.k) fwd1_gate(kt, ps, i, R);
+  }
+}
+
+}  // namespace slam

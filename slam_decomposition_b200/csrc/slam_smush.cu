@@ -1,11 +1,139 @@
-// placeholder until K4 lands
+// slam_smush.cu -- K4: templates whose 2Q gate is a time-sliced smush Hamiltonian (forward evaluation),
+// constant-gate lowering, and K4b: the parallel-drive Weyl trajectory.
+#include "slam_fwd1.cuh"
 #include "slam_host.h"
+#include "slam_weyl.cuh"
+
 namespace slam {
-int smush_eval_launch(const KTemplate&, const double*, int64_t, double*, int64_t, cudaStream_t) { return SLAM_ERR_UNSUPPORTED; }
-int lower_const_smush(const SlamTemplateDesc*, KTemplate*, cudaStream_t) { return SLAM_ERR_UNSUPPORTED; }
+
+// ---- K1 for parameter-bound smush templates: one thread per parameter row ---------------------------
+__global__ void __launch_bounds__(128) smush_eval_kernel(const __grid_constant__ KTemplate kt, const double* __restrict__ x,
+                                                         int64_t ldx, double* __restrict__ U, int64_t B) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  GlobalParams ps{x + b * ldx};
+  cd R[4][4];
+  fwd1_chain(kt, ps, R);
+  double* out = U + b * 32;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<double2*>(out + (r * 4 + c) * 2) = make_double2(R[c][r].re, R[c][r].im);
 }
-// temporary stubs (replaced as the kernels land)
-extern "C" {
-int slam_coverage_mc(const SlamTemplateDesc*, uint64_t, int64_t, int64_t, double, double, int32_t, unsigned long long*, double*, void*) { return SLAM_ERR_UNSUPPORTED; }
-int slam_pd_trajectory(const double*, const double*, const double*, int32_t, int32_t, double, int32_t, double*, double*, int64_t, void*) { return SLAM_ERR_UNSUPPORTED; }
+
+int smush_eval_launch(const KTemplate& kt, const double* x, int64_t ldx, double* U, int64_t B, cudaStream_t st) {
+  const unsigned grid = (unsigned)((B + 127) / 128);
+  smush_eval_kernel<<<grid, 128, 0, st>>>(kt, x, ldx, U, B);
+  SLAM_CUDA_CHECK(cudaGetLastError());
+  return SLAM_OK;
+}
+
+// ---- constant smush gates -> dense matrices (device computes them; no host expm) ---------------------
+struct ConstParams {
+  __device__ __forceinline__ double get(int) const { return 0.0; }
+};
+
+__global__ void const_smush_kernel(const __grid_constant__ KTemplate kt, double* __restrict__ out) {
+  const int g = threadIdx.x;
+  if (g >= kt.k) return;
+  cd R[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) R[c][r] = mkc(c == r ? 1.0 : 0.0, 0.0);
+  ConstParams ps;
+  fwd1_gate(kt, ps, g, R);
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      out[g * 32 + (r * 4 + c) * 2] = R[c][r].re;
+      out[g * 32 + (r * 4 + c) * 2 + 1] = R[c][r].im;
+    }
+}
+
+int lower_const_smush(const SlamTemplateDesc* d, KTemplate* kt, cudaStream_t st) {
+  (void)d;
+  KTemplate tmp = *kt;
+  tmp.gmode = GM_SMUSH;
+  double* dev = nullptr;
+  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&dev, sizeof(double) * 32 * SLAM_MAX_K, st));
+  const_smush_kernel<<<1, SLAM_MAX_K, 0, st>>>(tmp, dev);
+  SLAM_CUDA_CHECK(cudaGetLastError());
+  SLAM_CUDA_CHECK(cudaMemcpyAsync(kt->dense, dev, sizeof(double) * 32 * kt->k, cudaMemcpyDeviceToHost, st));
+  SLAM_CUDA_CHECK(cudaStreamSynchronize(st));
+  SLAM_CUDA_CHECK(cudaFreeAsync(dev, st));
+  kt->gmode = GM_DENSE;
+  return SLAM_OK;
+}
+
+// ---- K4b: Weyl trajectory of N smush1q slices, R sub-times each (pd_playground.py:179-208) -----------
+__global__ void __launch_bounds__(128) trajectory_kernel(const double* __restrict__ gate, const double* __restrict__ gx,
+                                                         const double* __restrict__ gy, int N, int Rn, double dt, int flags,
+                                                         double* __restrict__ coords, double* __restrict__ Ufinal, int64_t B) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* gp = gate + b * 8;
+  const SmushGate G = smush_gate(gp[0], gp[1], gp[2], gp[3], gp[4], gp[5], gp[6], gp[7]);
+  cd P[4][4];  // prefix product of the completed slices, [col][row]
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) P[c][r] = mkc(c == r ? 1.0 : 0.0, 0.0);
+  for (int s = 0; s < N; ++s) {
+    const double ax = gx[b * N + s], ay = gy[b * N + s];
+    for (int q = 0; q < Rn; ++q) {
+      // np.linspace(0, dt, R)[q]; the last point is exactly dt
+      const double t = (Rn == 1) ? 0.0 : ((q == Rn - 1) ? dt : dt * ((double)q / (double)(Rn - 1)));
+      const bool last = (q == Rn - 1);
+      if (!coords && !last) continue;
+      cd Y[4][4];
+      smush_slice(G, ax, ay, t, Y);
+      cd W[4][4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) W[c][r] = P[c][r];
+      left_mul(Y, W);
+      if (coords) {
+        cd M[4][4];  // [row][col]
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) M[r][c] = W[c][r];
+        double cc[3];
+        weyl_makhlin(M, flags, cc, nullptr);
+        double* o = coords + ((b * N + s) * Rn + q) * 3;
+        o[0] = cc[0];
+        o[1] = cc[1];
+        o[2] = cc[2];
+      }
+      if (last) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) P[c][r] = W[c][r];
+      }
+    }
+  }
+  if (Ufinal) {
+    double* out = Ufinal + b * 32;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) *reinterpret_cast<double2*>(out + (r * 4 + c) * 2) = make_double2(P[c][r].re, P[c][r].im);
+  }
+}
+
+}  // namespace slam
+
+extern "C" int slam_pd_trajectory(const double* gate, const double* gx, const double* gy, int32_t N, int32_t R, double dt,
+                                  int32_t flags, double* coords, double* Ufinal, int64_t B, void* stream) {
+  using namespace slam;
+  if (!gate || !gx || !gy || N < 1 || R < 1 || B < 0 || (!coords && !Ufinal)) return SLAM_ERR_INVALID;
+  if (B == 0) return SLAM_OK;
+  const unsigned grid = (unsigned)((B + 127) / 128);
+  trajectory_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gate, gx, gy, N, R, dt, flags, coords, Ufinal, B);
+  SLAM_CUDA_CHECK(cudaGetLastError());
+  return SLAM_OK;
 }

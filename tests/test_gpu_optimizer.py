@@ -1,0 +1,180 @@
+"""K5 + TemplateOptimizer shim: drop-in behaviour of the reference API and convergence parity with the oracle."""
+import logging
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from helpers import BASES, make_pair
+from slam_decomposition_b200 import engine
+from slam_decomposition_b200.basis import CircuitTemplate
+from slam_decomposition_b200.basis_abc import DataDictEntry
+from slam_decomposition_b200.basisv2 import CircuitTemplateV2
+from slam_decomposition_b200.cost_function import (BasicCost, BasicCostInverse, MakhlinEuclideanCost, MakhlinFunctionalCost,
+                                                   SquareCost, SquareReducedCost, WeylEuclideanCost)
+from slam_decomposition_b200.optimizer import TemplateOptimizer
+from slam_decomposition_b200.sampler import GateSample, HaarBatchSample, HaarSample
+from slam_decomposition_b200.utils.gates.custom_gates import (BerkeleyGate, CanonicalGate, ConversionGainGate, CXGate,
+                                                             RiSwapGate, SwapGate)
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_example_flow():
+    """README.md:33-51: CircuitTemplate(maximum_span_guess=4, preseed=False) + BasicCost + HaarSample(n_samples=1)."""
+    np.random.seed(0)
+    basis = CircuitTemplate(maximum_span_guess=4, preseed=False)
+    objective = BasicCost()
+    optimizer = TemplateOptimizer(basis=basis, objective=objective, use_callback=True)
+    sampler = HaarSample(seed=3, n_samples=1)
+    training_loss, coordinate_list, data = optimizer.approximate_from_distribution(sampler=sampler)
+    assert len(data) == 1 and isinstance(data[0], DataDictEntry)
+    d = data[0]
+    assert d.success_label == 1 and d.loss_result <= 1e-10 and d.cycles in (2, 3)
+    # the oracle confirms the returned parameters on the identical target
+    V = O.haar_sample_unitary(3)
+    tmpl = O.OracleTemplate("riswap", (0.5,), k=d.cycles)
+    assert len(d.Xk) == tmpl.n_params
+    assert O.cost(tmpl.eval(d.Xk), V, "basic") <= 1e-9
+    # flag format of training_loss (optimizer.py:238, parsed by visualize.py:90-117)
+    assert training_loss[0][0] == -1 and training_loss[0][1] == 1
+    assert optimizer.best_cycle_list == [d.cycles]
+    assert all(len(c) == 3 for c in coordinate_list[0])
+    # found coordinates equal the target's (locally equivalent gates)
+    assert np.allclose(O.fold_c1(np.array(O.c1c2c3(tmpl.eval(d.Xk)))), O.fold_c1(np.array(O.c1c2c3(V))), atol=1e-4)
+
+
+def test_b7_readme_target_solved_at_k2():
+    V = O.canonical_gate(0.58941013, 0.22184674, 0.11209285)
+    opt = TemplateOptimizer(CircuitTemplate(maximum_span_guess=4, preseed=False), BasicCost())
+    d = opt.approximate_target_U(V)
+    assert d.cycles == 2 and d.loss_result <= 1e-10
+
+
+@pytest.mark.parametrize("gate,k_expected", [(CXGate(), 2), (SwapGate(), 3), (BerkeleyGate(), 2),
+                                             (CanonicalGate(np.pi / 4, np.pi / 6, np.pi / 6), 3)])
+def test_known_gate_counts_with_sqrt_iswap(gate, k_expected):
+    """sqrt(iSWAP) needs 2 applications for CX / B and 3 for SWAP (Huang et al.; weyl_decompose.py in the reference)."""
+    opt = TemplateOptimizer(CircuitTemplate(maximum_span_guess=4, preseed=False), BasicCost(), training_restarts=16)
+    _, _, data = opt.approximate_from_distribution(GateSample(gate))
+    assert data[0].success_label == 1 and data[0].cycles == k_expected
+    tmpl = O.OracleTemplate("riswap", (0.5,), k=k_expected)
+    assert O.cost(tmpl.eval(data[0].Xk), np.asarray(gate), "basic") <= 1e-9
+
+
+def test_converges_wherever_the_reference_does():
+    """north_star: converged losses <= 1e-9 wherever the reference succeeds.  Reference = literal scipy-BFGS loop
+    (oracle.literal_run) on the same targets; success parity is one-sided (SURVEY hard parts)."""
+    n = 6
+    sampler = HaarBatchSample(seed=21, n_samples=n)
+    targets = list(sampler)
+    np.random.seed(1)
+    opt = TemplateOptimizer(CircuitTemplate(maximum_span_guess=3, preseed=False), BasicCost(), override_fail=True,
+                            training_restarts=5)
+    _, _, data = opt.approximate_from_distribution(sampler)
+    rng = np.random.default_rng(0)
+    for V, d in zip(targets, data):
+        ref = O.literal_run(lambda k: O.OracleTemplate("riswap", (0.5,), k=k), V, range(1, 4), restarts=5,
+                            success_threshold=1e-8, rng=rng)
+        if ref.best_result <= 1e-8:  # the FD-gradient reference typically stalls around 1e-9 (cost_function_comparison.ipynb)
+            assert d.loss_result <= 1e-9
+            assert d.cycles <= ref.best_cycles
+        tmpl = O.OracleTemplate("riswap", (0.5,), k=d.cycles)
+        assert abs(O.cost(tmpl.eval(d.Xk), V, "basic") - d.loss_result) < 1e-12  # reported loss is the true loss
+
+
+def test_failure_raises_value_error_unless_overridden():
+    basis = CircuitTemplate(maximum_span_guess=1, preseed=False)  # one sqrt(iSWAP) cannot make SWAP
+    with pytest.raises(ValueError, match="Failed to converge"):
+        TemplateOptimizer(basis, BasicCost()).approximate_from_distribution(GateSample(SwapGate()))
+    opt = TemplateOptimizer(basis, BasicCost(), override_fail=True)
+    loss, _, data = opt.approximate_from_distribution(GateSample(SwapGate()))
+    assert data[0].success_label == 0 and data[0].loss_result > 1e-3 and loss == [data[0].loss_result]
+
+
+def test_square_cost_and_v2_continuous_gate():
+    """decomp_trajectory.ipynb flow: CircuitTemplateV2(base_gates=[RiSwapGate]) with SquareCost onto SWAP."""
+    np.random.seed(2)
+    basis = CircuitTemplateV2(n_qubits=2, base_gates=[RiSwapGate], edge_params=[[(0, 1)]])
+    basis.build(3)
+    basis.spanning_range = range(3, 4)
+    assert [p.name for p in basis.circuit.parameters][-3:] == ["Q0", "Q1", "Q2"]
+    opt = TemplateOptimizer(basis=basis, objective=SquareCost(), use_callback=False, override_fail=True,
+                            success_threshold=1e-7, training_restarts=25)
+    d = opt.approximate_target_U(np.asarray(SwapGate()))
+    assert d.success_label == 1 and d.loss_result <= 1e-7 and d.cycles == 3
+    tmpl = O.OracleTemplate("riswap", ("Q",), k=3)
+    assert O.cost(tmpl.eval(d.Xk), O.SWAP, "square") <= 1e-7
+
+
+def test_unsupported_objectives_and_bounds_fail_loudly():
+    basis = CircuitTemplate(maximum_span_guess=2, preseed=False)
+    with pytest.raises(NotImplementedError):
+        TemplateOptimizer(basis, MakhlinFunctionalCost()).approximate_target_U(O.CNOT)
+    with pytest.raises(ValueError, match="Unrecognized Cost Function"):
+        TemplateOptimizer(basis, object()).approximate_target_U(O.CNOT)
+    b2 = CircuitTemplateV2(base_gates=[RiSwapGate])
+    b2.build(2)
+    b2.add_bound("Q0", 0.5, 0.0)
+    with pytest.raises(NotImplementedError):
+        TemplateOptimizer(b2, BasicCost()).approximate_target_U(O.CNOT)
+    with pytest.raises(ValueError):
+        b2.add_bound("Q99", 1, 0)
+    with pytest.raises(ValueError):
+        basis.build(0)
+
+
+def test_cost_functionals_match_oracle():
+    rng = np.random.default_rng(4)
+    U, V = O.haar_unitary(rng), O.haar_unitary(rng)
+    pairs = [(BasicCost(), "basic"), (SquareCost(), "square"), (BasicCostInverse(), "basic_inverse"),
+             (WeylEuclideanCost(), "weyl_euclidean"), (MakhlinEuclideanCost(), "makhlin_euclidean"),
+             (MakhlinFunctionalCost(), "makhlin_functional"), (SquareReducedCost(), "square_reduced")]
+    for obj, name in pairs:
+        assert obj.unitary_fidelity(U, V) == pytest.approx(O.cost(U, V, name), abs=2e-8), name
+        assert obj.normalization == 1
+    # B5b: quantised Makhlin functional (bit pattern) through the device kernel
+    assert MakhlinFunctionalCost().unitary_fidelity(O.SWAP, O.SWAP) == 0.0
+    with pytest.raises(ValueError):
+        WeylEuclideanCost().unitary_fidelity(np.eye(8), np.eye(8))
+
+
+def test_batched_sweep_statistics_sqcnot():
+    """Haar sweep onto sqCNOT templates: coverage fractions per k are a property of the basis gate
+    (reference data/extended_results.json has sqCNOT k=4 ~ 0.96 of the Haar volume)."""
+    np.random.seed(5)
+    gate = ConversionGainGate(0.0, 0.0, *BASES["sqCNOT"])
+    opt = TemplateOptimizer(CircuitTemplate(base_gates=[gate], maximum_span_guess=6, preseed=False), BasicCost(),
+                            override_fail=True, training_restarts=16)
+    V = np.stack(list(HaarBatchSample(seed=8, n_samples=3000)))
+    out = opt.approximate_targets(V)
+    assert out["success"].all()
+    frac = np.bincount(out["cycles"], minlength=7)[1:] / 3000.0
+    assert frac[0] == 0 and frac[1] == 0          # sqCNOT^1, sqCNOT^2 have zero Haar volume
+    assert 0.40 < frac[2] < 0.60                  # k=3
+    assert 0.93 < frac[:4].sum() < 0.98           # cumulative k<=4 ~ 0.96
+    assert frac[5] < 0.01
+    # every reported solution is verified by the oracle at the reported k
+    for i in (0, 1, 2, 3, 2999):
+        k = int(out["cycles"][i])
+        tmpl = O.OracleTemplate("cg", (0.0, 0.0, *BASES["sqCNOT"]), k=k)
+        assert O.cost(tmpl.eval(out["Xk"][i, : out["n_params"][i]]), V[i], "basic") <= 1e-9
+
+
+def test_lbfgs_with_explicit_x0_is_deterministic_and_matches_scipy_minimum():
+    desc, orc = make_pair("riswap", (0.5,), k=3)
+    rng = np.random.default_rng(12)
+    V = O.haar_unitary(rng, 4)
+    x0 = rng.uniform(0, 2 * np.pi, (4, 3, orc.n_params))
+    opts = engine.opt_defaults()
+    opts.early_exit = 0
+    a = engine.lbfgs_solve(desc, torch.as_tensor(V, device="cuda"), 3, opts, x0=torch.as_tensor(x0, device="cuda"))
+    b = engine.lbfgs_solve(desc, torch.as_tensor(V, device="cuda"), 3, opts, x0=torch.as_tensor(x0, device="cuda"))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    loss = a[0].cpu().numpy()
+    x = a[1].cpu().numpy()
+    for t in range(4):
+        for r in range(3):
+            assert abs(O.cost(orc.eval(x[t, r]), V[t], "basic") - loss[t, r]) < 1e-12
+    assert (loss.min(axis=1) < 1e-10).all()

@@ -1,0 +1,118 @@
+"""K4 parity: smush templates (per-slice exp(-i dt H)), constant-gate lowering, gate __array__, trajectory."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from helpers import BASES, make_pair
+from slam_decomposition_b200 import engine
+from slam_decomposition_b200.hamiltonian import ConversionGainPhaseHamiltonian, ConversionGainSmush, ConversionGainSmush1QPhase
+from slam_decomposition_b200.utils.gates.custom_gates import (
+    BerkeleyGate, CanonicalGate, ConversionGainGate, ConversionGainSmush1QPhaseGate, ConversionGainSmushGate, RiSwapGate)
+
+pytestmark = pytest.mark.gpu
+TOL_U = 1e-10
+
+
+def _dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+
+
+@pytest.mark.parametrize("base,T", [("sqiSwap", 2), ("iSwap", 4), ("sqCNOT", 2), ("B", 4)])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_mc_smush_template_matches_oracle(base, T, k):
+    """The coverage template of parallel_drive_volume.py:175-198: no exterior 1Q, Q = (phi_c, phi_g, gx[T], gy[T])."""
+    gc, gg, t = BASES[base]
+    slots = ("Q", "Q", gc, gg) + ("Q",) * (2 * T) + (t,)
+    desc, orc = make_pair("smush", slots, k=k, T=T, no_exterior_1q=True)
+    assert orc.n_params == 6 * (k - 1) + k * (2 + 2 * T)
+    rng = np.random.default_rng(k)
+    X = rng.uniform(-4 * np.pi, 4 * np.pi, (40, orc.n_params))
+    U = engine.template_eval(desc, _dev(X)).cpu().numpy()
+    Uo = orc.eval_batch(X)
+    assert np.abs(U - Uo).max() < TOL_U
+    assert np.abs(np.einsum("bij,bkj->bik", U, U.conj()) - np.eye(4)).max() < 1e-12
+
+
+def test_smush1q_template_and_partial_binding():
+    T = 3
+    slots = (0.3, "Q", -0.2, 0.5, np.pi / 2, 0.1, "Q", 0.4) + ("Q",) * T + (0.7, "Q", -1.1) + ("Q",)
+    desc, orc = make_pair("smush1q", slots, k=2, T=T)
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-3, 3, (25, orc.n_params))
+    U = engine.template_eval(desc, _dev(X)).cpu().numpy()
+    assert np.abs(U - orc.eval_batch(X)).max() < TOL_U
+
+
+def test_constant_smush_gate_is_lowered_on_device_and_differentiable():
+    """All-constant smush gates become dense matrices computed by the device; loss/grad then run the adjoint."""
+    T = 2
+    slots = (0.2, -0.3, np.pi / 2, 0.0, 1.0, -2.0, 0.5, 0.25, 0.5)
+    desc, orc = make_pair("smush", slots, k=2, T=T)
+    rng = np.random.default_rng(6)
+    X = rng.uniform(0, 2 * np.pi, (10, orc.n_params))
+    V = O.haar_unitary(rng, 3)
+    U = engine.template_eval(desc, _dev(X)).cpu().numpy()
+    assert np.abs(U - orc.eval_batch(X)).max() < TOL_U
+    loss, grad, _ = engine.loss_grad(desc, _dev(X), _dev(V))
+    for b in range(10):
+        l, g, _ = O.loss_and_grad(orc, X[b], V[b % 3])
+        assert abs(loss[b].item() - l) < 1e-12 and np.abs(grad[b].cpu().numpy() - g).max() < 1e-10
+
+
+def test_large_drive_amplitudes_need_many_squarings():
+    slots = ("Q", "Q", np.pi / 2, 0.0, "Q", "Q", 1.0)
+    desc, orc = make_pair("smush", slots, k=1, T=1, no_exterior_1q=True)
+    X = np.array([[0.1, -0.2, 200.0, -150.0], [3.0, 1.0, 1e-9, 0.0], [0.0, 0.0, 0.0, 0.0]])
+    U = engine.template_eval(desc, _dev(X)).cpu().numpy()
+    assert np.abs(U - orc.eval_batch(X)).max() < 1e-9  # ||dt H|| ~ 350: error grows with the 11 squarings
+
+
+def test_gate_objects_give_device_matrices():
+    assert np.abs(np.asarray(RiSwapGate(0.5)) - O.riswap(0.5)).max() < 1e-15
+    assert np.abs(np.asarray(ConversionGainGate(0.3, -0.2, 1.1, 0.4, 0.7)) - O.conversion_gain(0.3, -0.2, 1.1, 0.4, 0.7)).max() < 1e-15
+    g = ConversionGainSmushGate(0.1, 0.2, 1.0, 0.5, [0.3, -0.4], [1.0, 2.0], 0.5)
+    assert np.abs(np.asarray(g) - O.smush(0.1, 0.2, 1.0, 0.5, [0.3, -0.4], [1.0, 2.0], 0.5)).max() < TOL_U
+    g1 = ConversionGainSmush1QPhaseGate(0.1, 0.2, 0.3, 0.4, 1.0, 0.5, 0.3, -0.2, [1.0, -2.0, 0.5], [0.3, 0.1, -1.0], 1.5)
+    ref = O.smush_1qphase(0.1, 0.2, 0.3, 0.4, 1.0, 0.5, 0.3, -0.2, [1.0, -2.0, 0.5], [0.3, 0.1, -1.0], 1.5)
+    assert np.abs(np.asarray(g1) - ref).max() < TOL_U
+    assert np.abs(np.asarray(BerkeleyGate()) - O.berkeley()).max() < 1e-15
+    assert np.abs(np.asarray(CanonicalGate(0.3, 0.2, 0.1)) - O.canonical_gate(0.6 / np.pi, 0.4 / np.pi, 0.2 / np.pi)).max() < 1e-15
+    assert g.cost() == pytest.approx(1.5 * 0.5 / (np.pi / 2))
+
+
+def test_hamiltonian_factories_keep_reference_conventions():
+    # positional quirk of ConversionGainPhaseHamiltonian.construct_U
+    U = ConversionGainPhaseHamiltonian.construct_U(0.3, -0.2, 1.1, 0.4, t=0.7)
+    assert np.abs(U - O.conversion_gain(0.3, -0.2, 1.1, 0.4, 0.7)).max() < 1e-15
+    U = ConversionGainSmush.construct_U(0.1, 0.2, 1.0, 0.5, [0.3, -0.4], [1.0, 2.0], t=0.5)
+    assert np.abs(U - O.smush(0.1, 0.2, 1.0, 0.5, [0.3, -0.4], [1.0, 2.0], 0.5)).max() < TOL_U
+    U = ConversionGainSmush1QPhase.construct_U(0.1, 0.2, 0.3, 0.4, 1.0, 0.5, 0.3, -0.2, [1.0], [0.3], t=0.1)
+    assert np.abs(U - O.smush_1qphase(0.1, 0.2, 0.3, 0.4, 1.0, 0.5, 0.3, -0.2, [1.0], [0.3], 0.1)).max() < TOL_U
+
+
+def test_trajectory_matches_iterate_time():
+    rng = np.random.default_rng(9)
+    B, N, R, dt = 6, 10, 5, 0.1
+    gate = np.zeros((B, 8))
+    gate[:, :4] = rng.uniform(-1, 1, (B, 4))
+    gate[:, 4] = np.pi / 2
+    gate[:, 5] = rng.uniform(0, 0.5, B)
+    gate[:, 6:] = rng.uniform(-0.5, 0.5, (B, 2))
+    gate[0, :4] = 0.0
+    gate[0, 5:] = 0.0  # the widget default: iSWAP drive, no phases
+    gx = rng.uniform(-2 * np.pi, 2 * np.pi, (B, N))
+    gy = rng.uniform(-2 * np.pi, 2 * np.pi, (B, N))
+    coords, Uf = engine.pd_trajectory(_dev(gate), _dev(gx), _dev(gy), dt, R=R, fold=True, round8=False)
+    coords, Uf = coords.cpu().numpy(), Uf.cpu().numpy()
+    for b in range(B):
+        ref_c, ref_U = O.trajectory(gate[b, :4], gate[b, 4], gate[b, 5], gate[b, 6], gate[b, 7], gx[b], gy[b], dt, R)
+        assert np.abs(Uf[b] - ref_U).max() < TOL_U
+        # the oracle rounds to 8 dp like the reference; compare the un-rounded device coordinates against it
+        assert np.abs(coords[b] - ref_c).max() < 1e-8
+    # rounded + folded output equals the reference's stored values except at rounding ties
+    c8, _ = engine.pd_trajectory(_dev(gate), _dev(gx), _dev(gy), dt, R=R, fold=True, round8=True)
+    ref_all = np.stack([O.trajectory(gate[b, :4], gate[b, 4], gate[b, 5], gate[b, 6], gate[b, 7], gx[b], gy[b], dt, R)[0]
+                        for b in range(B)])
+    assert np.mean(np.abs(c8.cpu().numpy() - ref_all) < 1e-12) > 0.97
+    assert np.abs(c8.cpu().numpy() - ref_all).max() <= 1.0000001e-8
