@@ -9,6 +9,14 @@ void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
+int keep_async_pool(int device) {
+  cudaMemPool_t pool;
+  SLAM_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long keep = ~0ULL;
+  SLAM_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  return SLAM_OK;
+}
+
 static int expected_slots(int kind, int T) {
   switch (kind) {
     case SLAM_GATE_RISWAP: return 1;
@@ -57,6 +65,16 @@ int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_
     any_bound |= bound;
   }
   kt->n_trig = 6 * (d->k + 1);
+  {  // each Xk entry may be bound to at most one slot (qiskit Parameters are created once per slot, basis.py:136-169);
+     // the gradient kernels store, rather than accumulate, each partial derivative
+    unsigned char used[SLAM_MAX_PARAMS] = {0};
+    for (int i = 0; i <= d->k; ++i)
+      for (int s = 0; s < 6; ++s)
+        if (kt->p1q[i][s] >= 0 && used[kt->p1q[i][s]]++) return SLAM_ERR_UNSUPPORTED;
+    for (int g = 0; g < d->k; ++g)
+      for (int s = 0; s < ns; ++s)
+        if (kt->slot_param[g][s] >= 0 && used[kt->slot_param[g][s]]++) return SLAM_ERR_UNSUPPORTED;
+  }
 
   if (d->gate_kind == SLAM_GATE_FIXED) {
     kt->gmode = GM_DENSE;

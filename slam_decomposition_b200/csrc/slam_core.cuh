@@ -195,6 +195,42 @@ __device__ __forceinline__ double team_max(double v) {
   return v;
 }
 
+// Sum six per-lane partials over the team and leave each total on exactly one lane (reduce-scatter):
+// 5 double shuffles instead of the 12 of a full butterfly, and the stores are spread over the lanes.
+//   LPP = 4: lane 0 owns {0,1}, lane 1 {2}, lane 2 {3,4}, lane 3 {5};  LPP = 2: lane 0 {0,1,2}, lane 1 {3,4,5}.
+template <int LPP, class Store>
+__device__ __forceinline__ void reduce_scatter6(const double d[6], int sub, Store store) {
+  if (LPP == 1) {
+#pragma unroll
+    for (int s = 0; s < 6; ++s) store(s, d[s]);
+  } else if (LPP == 2) {
+    const bool hi = sub & 1;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const double keep = hi ? d[3 + t] : d[t], give = hi ? d[t] : d[3 + t];
+      const double v = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+      store(hi ? 3 + t : t, v);
+    }
+  } else {
+    const bool up = sub & 2, hi = sub & 1;
+    double m[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      const double keep = up ? d[3 + t] : d[t], give = up ? d[t] : d[3 + t];
+      m[t] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+    }
+    const int b = up ? 3 : 0;
+    const double v = __shfl_xor_sync(0xffffffffu, hi ? m[0] : m[2], 1);
+    const double w = m[1] + __shfl_xor_sync(0xffffffffu, m[1], 1);
+    if (hi) {
+      store(b + 2, m[2] + v);
+    } else {
+      store(b + 0, m[0] + v);
+      store(b + 1, w);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // trig cache: entry e < 6(k+1): layer e/6, slot e%6 (q0: theta/2, phi, lam; q1: theta/2, phi, lam)
 //             entries 6(k+1)+4g+{0,1,2,3}: gate g: phi_c, phi_g, a_c, a_g   (parameter-bound block gates)
@@ -315,7 +351,8 @@ __device__ __forceinline__ void cost_from_abs(int cost_kind, double a, double& l
 // loss + analytic gradient for one problem, executed by a team.
 //   xs : this problem's parameters (API order)            [shared or global]
 //   tg : this problem's trig cache, n_trig entries        [shared]  (filled here)
-//   gs : this problem's gradient (API order), written if WANT_GRAD
+//   gs : this problem's gradient (API order), written if WANT_GRAD.  Every parameter is bound to exactly one
+//        slot (checked on the host), so each entry is stored once; unused entries keep the zero fill.
 //   vcol[c][a] = V[a][sub*CPL + c]  (this lane's target columns)
 // returns loss (identical on every lane of the team); *T_out = Tr(V^dag U)
 // ------------------------------------------------------------------------------------------------
@@ -421,14 +458,18 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
           d[3 * q + 2] = -(m01e.im + m11e.im);
         }
       }
-#pragma unroll
-      for (int s = 0; s < 6; ++s) d[s] = team_sum<LPP>(d[s]);
-      if (sub == 0) {
-#pragma unroll
-        for (int s = 0; s < 6; ++s) {
-          const int p = kt.p1q[i][s];
-          if (p >= 0) gs[p] += d[s];
+      if (kt.vz_only) {
+        d[0] = team_sum<LPP>(d[0]);
+        d[3] = team_sum<LPP>(d[3]);
+        if (sub == 0) {
+          if (kt.p1q[i][0] >= 0) gs[kt.p1q[i][0]] = d[0];
+          if (kt.p1q[i][3] >= 0) gs[kt.p1q[i][3]] = d[3];
         }
+      } else {
+        reduce_scatter6<LPP>(d, sub, [&](int s, double v) {
+          const int p = kt.p1q[i][s];
+          if (p >= 0) gs[p] = v;
+        });
       }
     }
     if (i > 0) {
@@ -468,15 +509,15 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
         if (sub == 0) {
           if (kt.gate_kind == SLAM_GATE_RISWAP) {
             const int p = kt.slot_param[g][0];
-            if (p >= 0) gs[p] += 1.5707963267948966 * d_ac;
+            if (p >= 0) gs[p] = 1.5707963267948966 * d_ac;
           } else {
             const double gc = slot_value(kt, xs, g, 2), gg = slot_value(kt, xs, g, 3), tt = slot_value(kt, xs, g, 4);
             int p;
-            if ((p = kt.slot_param[g][0]) >= 0) gs[p] += d_pc;
-            if ((p = kt.slot_param[g][1]) >= 0) gs[p] += d_pg;
-            if ((p = kt.slot_param[g][2]) >= 0) gs[p] += tt * d_ac;
-            if ((p = kt.slot_param[g][3]) >= 0) gs[p] += tt * d_ag;
-            if ((p = kt.slot_param[g][4]) >= 0) gs[p] += gc * d_ac + gg * d_ag;
+            if ((p = kt.slot_param[g][0]) >= 0) gs[p] = d_pc;
+            if ((p = kt.slot_param[g][1]) >= 0) gs[p] = d_pg;
+            if ((p = kt.slot_param[g][2]) >= 0) gs[p] = tt * d_ac;
+            if ((p = kt.slot_param[g][3]) >= 0) gs[p] = tt * d_ag;
+            if ((p = kt.slot_param[g][4]) >= 0) gs[p] = gc * d_ac + gg * d_ag;
           }
         }
       }

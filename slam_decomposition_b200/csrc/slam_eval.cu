@@ -183,8 +183,9 @@ using namespace slam;
 
 extern "C" int slam_template_eval(const SlamTemplateDesc* desc, const double* x, int64_t ldx, double* U, int64_t B,
                                   void* stream) {
-  if (!desc || !U || B < 0 || (desc->n_params > 0 && !x) || ldx < desc->n_params) return SLAM_ERR_INVALID;
+  if (!desc || B < 0 || ldx < desc->n_params) return SLAM_ERR_INVALID;
   if (B == 0) return SLAM_OK;
+  if (!U || (desc->n_params > 0 && !x)) return SLAM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
   int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true);
@@ -205,10 +206,11 @@ extern "C" int slam_template_eval(const SlamTemplateDesc* desc, const double* x,
 extern "C" int slam_loss_grad(const SlamTemplateDesc* desc, const double* x, int64_t ldx, const double* V, int64_t Nt,
                               const int32_t* tgt_idx, int32_t cost_kind, double* loss, double* grad, int64_t ldg,
                               double* trace, int64_t B, void* stream) {
-  if (!desc || !V || !loss || Nt <= 0 || B < 0 || (desc->n_params > 0 && !x) || ldx < desc->n_params) return SLAM_ERR_INVALID;
+  if (!desc || B < 0 || ldx < desc->n_params) return SLAM_ERR_INVALID;
   if (grad && ldg < desc->n_params) return SLAM_ERR_INVALID;
   if (cost_kind < SLAM_COST_BASIC || cost_kind > SLAM_COST_BASIC_INVERSE) return SLAM_ERR_INVALID;  // optimizer.py:211
-  if (B == 0) return SLAM_OK;
+  if (B == 0) return SLAM_OK;  // empty batch: nothing to read or write
+  if (!V || !loss || Nt <= 0 || (desc->n_params > 0 && !x)) return SLAM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
   int rc = compile_template(desc, &kt, /*allow_bound_smush=*/false);

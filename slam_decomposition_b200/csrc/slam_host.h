@@ -29,4 +29,9 @@ int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_
 // gates to GM_DENSE by running the device smush kernel once (see slam_smush.cu).
 int lower_const_smush(const SlamTemplateDesc* d, KTemplate* kt, cudaStream_t stream);
 
+// cudaMallocAsync scratch is used for small per-call work areas.  With the default release threshold (0) every
+// synchronisation returns the pool to the OS and the next call pays for re-mapping it (measured on B200: stalls of
+// 0.1-1 s per sweep step); raise the threshold so freed blocks stay in the device's default pool.
+int keep_async_pool(int device);
+
 }  // namespace slam

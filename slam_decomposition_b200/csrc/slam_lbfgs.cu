@@ -10,7 +10,9 @@
 //
 // Warp-level structure: each "tick" every team of the warp performs exactly one loss+gradient evaluation
 // (the expensive, fully convergent part), then runs its own cheap, possibly divergent, line-search /
-// history bookkeeping.
+// history bookkeeping.  In the bookkeeping each lane owns the vector entries j = sub + 4 i (i < NPL) and keeps
+// its slice of the two-loop working vector in registers, so the recursion is a stream of independent
+// shared-memory loads and FMAs with one 2-stage shuffle reduction per history pair.
 #include <cfloat>
 
 #include "slam_host.h"
@@ -19,6 +21,7 @@
 namespace slam {
 
 constexpr int LPP = 4;
+constexpr int kMaxHist = 8;
 constexpr double kArmijo = 1e-4;
 
 struct LbfgsArgs {
@@ -56,7 +59,8 @@ __device__ __forceinline__ double tmax(double v, unsigned mask) {
 
 enum { ST_IDLE = 0, ST_INIT = 1, ST_LS = 2 };
 
-template <int GM>
+// NPL = vector entries per lane held in registers (P <= 4 * NPL)
+template <int GM, int NPL>
 __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ KTemplate kt,
                                                        const __grid_constant__ LbfgsArgs A) {
   extern __shared__ __align__(16) double smem[];
@@ -71,8 +75,7 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
   double* S = base + 5 * P;
   double* Y = S + m * P;
   double* rho = Y + m * P;
-  double* alp = rho + m;
-  double2* tg = reinterpret_cast<double2*>(alp + m + ((5 * P) & 1));
+  double2* tg = reinterpret_cast<double2*>(rho + m + ((5 * P + m) & 1));
 
   const int64_t total = A.Nt * (int64_t)A.restarts;
   // team-uniform scalars
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
         for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = 0.0;
         continue;
       }
-      // initial point into the trial buffer (buffer cur^1), target columns into registers
+      // initial point into the trial buffer (buffer 1), target columns into registers
       cur = 0;
       double* xt = base + 2 * P;
       for (int j = sub; j < P; j += LPP)
@@ -137,43 +140,50 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
     ++evals;
 
     // ---------------- per-team bookkeeping (divergent across teams) ------------------------------
-    double* x = base + 2 * cur * P;
-    double* g = x + P;
-    bool accepted = false;
-    if (state == ST_INIT) {
-      accepted = true;
-    } else if (ft <= f + kArmijo * alpha * gd) {  // Armijo; NaN compares false
-      accepted = true;
-      // history pair: s = xt - x, y = gt - g
-      double* s = S + hpos * P;
-      double* y = Y + hpos * P;
-      double sy = 0.0, yy = 0.0;
-      for (int j = sub; j < P; j += LPP) {
-        const double sj = xt[j] - x[j], yj = gt[j] - g[j];
-        s[j] = sj;
-        y[j] = yj;
-        sy = fma(sj, yj, sy);
-        yy = fma(yj, yj, yy);
-      }
-      sy = tsum(sy, tmask);
-      yy = tsum(yy, tmask);
-      if (sy > 1e-14 * yy && yy > 0.0) {  // cautious update: keep only positive-curvature pairs
-        if (sub == 0) rho[hpos] = 1.0 / sy;
-        gamma = sy / yy;
-        hpos = (hpos + 1 == m) ? 0 : hpos + 1;
-        hcount = min(hcount + 1, m);
-      }
-      ++iter;
-    }
+    const double* x = base + 2 * cur * P;
+    const double* g = x + P;
+    const bool first = (state == ST_INIT);
+    const bool accepted = first || (ft <= f + kArmijo * alpha * gd);  // Armijo; NaN compares false
     bool done = false;
+    double q[NPL];  // this lane's slice of the working vector (entries j = sub + 4 i)
     if (accepted) {
-      cur ^= 1;  // trial point becomes the current point
-      x = xt;
-      g = gt;
-      f = ft;
-      double gmax = 0.0;
-      for (int j = sub; j < P; j += LPP) gmax = fmax(gmax, fabs(g[j]));
+      // history pair s = xt - x, y = gt - g into slot hpos; q <- gt
+      double* s_new = S + hpos * P;
+      double* y_new = Y + hpos * P;
+      double sy = 0.0, yy = 0.0, gmax = 0.0;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int j = sub + LPP * i;
+        q[i] = 0.0;
+        if (j < P) {
+          const double gj = gt[j];
+          q[i] = gj;
+          gmax = fmax(gmax, fabs(gj));
+          if (!first) {
+            const double sj = xt[j] - x[j], yj = gj - g[j];
+            s_new[j] = sj;
+            y_new[j] = yj;
+            sy = fma(sj, yj, sy);
+            yy = fma(yj, yj, yy);
+          }
+        }
+      }
       gmax = tmax(gmax, tmask);
+      if (!first) {
+        sy = tsum(sy, tmask);
+        yy = tsum(yy, tmask);
+        if (sy > 1e-14 * yy && yy > 0.0) {  // cautious update: keep only positive-curvature pairs
+          if (sub == 0) rho[hpos] = 1.0 / sy;
+          gamma = sy / yy;
+          hpos = (hpos + 1 == m) ? 0 : hpos + 1;
+          hcount = min(hcount + 1, m);
+        } else if (hcount == m) {
+          hcount = m - 1;  // the rejected pair overwrote the oldest slot
+        }
+        ++iter;
+      }
+      cur ^= 1;  // trial point becomes the current point
+      f = ft;
       // progress checkpoint every 32 accepted steps: "slow" = less than 4x reduction since the last one
       if ((iter & 31) == 0) {
         slow = iter > 0 && f > 0.25 * f_chk;
@@ -184,48 +194,80 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
       // restarts still converging towards zero loss run on to f_stop / gtol.
       done = (f < A.f_stop) || (gmax < A.gtol) || (gmax < A.gtol_far && (f > A.f_far || slow)) ||
              (iter >= A.max_iter) || !(f == f);
-      if (!done && A.early_exit) done = *((volatile int32_t*)(A.solved + pid / A.restarts)) != 0;
+      if (!done && A.early_exit && (iter & 3) == 0) done = *((volatile int32_t*)(A.solved + pid / A.restarts)) != 0;
       if (!done) {
-        __syncwarp(tmask);
-        // two-loop recursion: D <- -H g
-        for (int j = sub; j < P; j += LPP) D[j] = g[j];
-        __syncwarp(tmask);
-        for (int h = 0; h < hcount; ++h) {
-          int slot = hpos - 1 - h;
-          if (slot < 0) slot += m;
-          const double* s = S + slot * P;
-          const double* y = Y + slot * P;
-          double a = 0.0;
-          for (int j = sub; j < P; j += LPP) a = fma(s[j], D[j], a);
-          a = tsum(a, tmask) * rho[slot];
-          if (sub == 0) alp[slot] = a;
-          for (int j = sub; j < P; j += LPP) D[j] = fma(-a, y[j], D[j]);
+        __syncwarp(tmask);  // s_new / y_new / rho visible to the team
+        // two-loop recursion on the register slice: q <- H g
+        double al[kMaxHist];
+#pragma unroll
+        for (int h = 0; h < kMaxHist; ++h) {
+          al[h] = 0.0;
+          if (h < hcount) {
+            int slot = hpos - 1 - h;
+            if (slot < 0) slot += m;
+            const double* s = S + slot * P;
+            const double* y = Y + slot * P;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NPL; i += 2) {
+              const int j0 = sub + LPP * i, j1 = j0 + LPP;
+              if (j0 < P) a0 = fma(s[j0], q[i], a0);
+              if (i + 1 < NPL && j1 < P) a1 = fma(s[j1], q[i + 1], a1);
+            }
+            const double a = tsum(a0 + a1, tmask) * rho[slot];
+            al[h] = a;
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+              const int j = sub + LPP * i;
+              if (j < P) q[i] = fma(-a, y[j], q[i]);
+            }
+          }
         }
-        __syncwarp(tmask);
-        for (int j = sub; j < P; j += LPP) D[j] *= gamma;
-        for (int h = hcount - 1; h >= 0; --h) {
-          int slot = hpos - 1 - h;
-          if (slot < 0) slot += m;
-          const double* s = S + slot * P;
-          const double* y = Y + slot * P;
-          double b = 0.0;
-          for (int j = sub; j < P; j += LPP) b = fma(y[j], D[j], b);
-          b = tsum(b, tmask) * rho[slot];
-          const double c = alp[slot] - b;
-          for (int j = sub; j < P; j += LPP) D[j] = fma(c, s[j], D[j]);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) q[i] *= gamma;
+#pragma unroll
+        for (int h = kMaxHist - 1; h >= 0; --h) {
+          if (h < hcount) {
+            int slot = hpos - 1 - h;
+            if (slot < 0) slot += m;
+            const double* s = S + slot * P;
+            const double* y = Y + slot * P;
+            double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NPL; i += 2) {
+              const int j0 = sub + LPP * i, j1 = j0 + LPP;
+              if (j0 < P) b0 = fma(y[j0], q[i], b0);
+              if (i + 1 < NPL && j1 < P) b1 = fma(y[j1], q[i + 1], b1);
+            }
+            const double c = al[h] - tsum(b0 + b1, tmask) * rho[slot];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+              const int j = sub + LPP * i;
+              if (j < P) q[i] = fma(c, s[j], q[i]);
+            }
+          }
         }
+        // d = -q ; gd = g.d ; gg = g.g  (g = gt: the accepted gradient)
         double gdn = 0.0, gg = 0.0;
-        for (int j = sub; j < P; j += LPP) {
-          const double dj = -D[j];
-          D[j] = dj;
-          gdn = fma(g[j], dj, gdn);
-          gg = fma(g[j], g[j], gg);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int j = sub + LPP * i;
+          if (j < P) {
+            const double gj = gt[j];
+            q[i] = -q[i];
+            gdn = fma(gj, q[i], gdn);
+            gg = fma(gj, gj, gg);
+          }
         }
         gdn = tsum(gdn, tmask);
         gg = tsum(gg, tmask);
         if (hcount == 0 || !(gdn < 0.0)) {  // first step or not a descent direction: steepest descent, unit length
           hcount = 0;
-          for (int j = sub; j < P; j += LPP) D[j] = -g[j];
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const int j = sub + LPP * i;
+            if (j < P) q[i] = -gt[j];
+          }
           gdn = -gg;
           alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
         } else {
@@ -234,11 +276,29 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
         gd = gdn;
         ls = 0;
         state = ST_LS;
+        // store the direction and the next trial point x_new = xt + alpha d (into the old current buffer)
+        double* xn = base + 2 * (cur ^ 1) * P;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int j = sub + LPP * i;
+          if (j < P) {
+            D[j] = q[i];
+            xn[j] = fma(alpha, q[i], xt[j]);
+          }
+        }
       }
     } else {
       // backtrack with the cubic through (0, f, gd) and (alpha, ft, gdt), safeguarded to [0.1, 0.5] alpha
       double gdt = 0.0;
-      for (int j = sub; j < P; j += LPP) gdt = fma(gt[j], D[j], gdt);
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int j = sub + LPP * i;
+        q[i] = 0.0;
+        if (j < P) {
+          q[i] = D[j];
+          gdt = fma(gt[j], q[i], gdt);
+        }
+      }
       gdt = tsum(gdt, tmask);
       double an = 0.5 * alpha;
       if (ft == ft && gdt == gdt) {
@@ -259,9 +319,15 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
         if (hcount > 0) {  // curvature model is bad: restart from steepest descent
           hcount = 0;
           double gg = 0.0;
-          for (int j = sub; j < P; j += LPP) {
-            D[j] = -g[j];
-            gg = fma(g[j], g[j], gg);
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const int j = sub + LPP * i;
+            if (j < P) {
+              const double gj = g[j];
+              q[i] = -gj;
+              D[j] = -gj;
+              gg = fma(gj, gj, gg);
+            }
           }
           gg = tsum(gg, tmask);
           gd = -gg;
@@ -271,28 +337,50 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
           done = true;  // no progress possible at working precision
         }
       }
+      if (!done) {
+        double* xn = base + 2 * (cur ^ 1) * P;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int j = sub + LPP * i;
+          if (j < P) xn[j] = fma(alpha, q[i], x[j]);
+        }
+      }
     }
     if (done) {
+      const double* xf = base + 2 * cur * P;
       if (sub == 0) {
         A.out_loss[pid] = f;
         A.out_iters[pid] = iter;
         if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + pid / A.restarts, 1);
       }
-      for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = x[j];
+      for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = xf[j];
       state = ST_IDLE;
-    } else {
-      __syncwarp(tmask);
-      double* xn = base + 2 * (cur ^ 1) * P;
-      for (int j = sub; j < P; j += LPP) xn[j] = fma(alpha, D[j], x[j]);
     }
   }
   if (A.out_evals && sub == 0 && evals) atomicAdd(A.out_evals, evals);
 }
 
 static int team_doubles(const KTemplate& kt, int m) {
-  int rs = (5 + 2 * m) * kt.P + 2 * m + ((5 * kt.P) & 1) + 2 * kt.n_trig;
+  int rs = (5 + 2 * m) * kt.P + m + ((5 * kt.P + m) & 1) + 2 * kt.n_trig;
   while ((rs & 15) != 4) ++rs;  // 4 (mod 16): the 4 teams of a half-warp hit disjoint bank groups
   return rs;
+}
+
+template <int GM, int NPL>
+static int launch_lbfgs(const KTemplate& kt, const LbfgsArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
+  auto kern = lbfgs_kernel<GM, NPL>;
+  SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, threads, smem, st>>>(kt, A);
+  SLAM_CUDA_CHECK(cudaGetLastError());
+  return SLAM_OK;
+}
+
+template <int GM>
+static int dispatch_npl(const KTemplate& kt, const LbfgsArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
+  if (kt.P <= 32) return launch_lbfgs<GM, 8>(kt, A, grid, threads, smem, st);
+  if (kt.P <= 56) return launch_lbfgs<GM, 14>(kt, A, grid, threads, smem, st);
+  if (kt.P <= 96) return launch_lbfgs<GM, 24>(kt, A, grid, threads, smem, st);
+  return SLAM_ERR_UNSUPPORTED;  // the device optimiser keeps 4*NPL <= 96 parameters in registers
 }
 
 }  // namespace slam
@@ -321,13 +409,14 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   if (!desc || !V || !opts || !out_loss || !out_x || !out_iters || Nt < 0 || restarts < 1) return SLAM_ERR_INVALID;
   if (x0 && ldx0 < desc->n_params) return SLAM_ERR_INVALID;
   if (opts->cost_kind != SLAM_COST_BASIC && opts->cost_kind != SLAM_COST_SQUARE) return SLAM_ERR_UNSUPPORTED;
-  if (opts->max_iter < 1 || opts->history < 0 || opts->history > 8) return SLAM_ERR_INVALID;
+  if (opts->max_iter < 1 || opts->history < 0 || opts->history > kMaxHist) return SLAM_ERR_INVALID;
   if (desc->n_params < 1) return SLAM_ERR_INVALID;
   if (Nt == 0) return SLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
   int rc = compile_template(desc, &kt, /*allow_bound_smush=*/false);
   if (rc != SLAM_OK) return rc;
+  if (kt.P > 96) return SLAM_ERR_UNSUPPORTED;
   if (kt.gmode == GM_DENSE && desc->gate_kind != SLAM_GATE_FIXED) {
     rc = lower_const_smush(desc, &kt, st);
     if (rc != SLAM_OK) return rc;
@@ -346,6 +435,9 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   const size_t smem = (size_t)RS * 8 * teams;
   if (smem > (size_t)max_smem) return SLAM_ERR_UNSUPPORTED;
 
+  // stream-ordered scratch: work counter + per-target early-exit flags
+  rc = keep_async_pool(dev);
+  if (rc != SLAM_OK) return rc;
   unsigned long long* next = nullptr;
   int32_t* solved = nullptr;
   SLAM_CUDA_CHECK(cudaMallocAsync((void**)&next, sizeof(unsigned long long), st));
@@ -362,23 +454,15 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   A.next = next; A.solved = solved;
 
   const int64_t total = Nt * (int64_t)restarts;
-  int grid = (int)std::min<int64_t>((int64_t)sms, (total + teams - 1) / teams);
+  const int grid = (int)std::min<int64_t>((int64_t)sms, (total + teams - 1) / teams);
   const int threads = teams * LPP;
-#define SLAM_LAUNCH_LBFGS(GMV)                                                                                    \
-  do {                                                                                                            \
-    auto kern = lbfgs_kernel<GMV>;                                                                                \
-    SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-    kern<<<grid, threads, smem, st>>>(kt, A);                                                                     \
-  } while (0)
   switch (kt.gmode) {
-    case GM_SYM: SLAM_LAUNCH_LBFGS(GM_SYM); break;
-    case GM_BLOCK: SLAM_LAUNCH_LBFGS(GM_BLOCK); break;
-    case GM_DENSE: SLAM_LAUNCH_LBFGS(GM_DENSE); break;
-    default: cudaFreeAsync(next, st); cudaFreeAsync(solved, st); return SLAM_ERR_UNSUPPORTED;
+    case GM_SYM: rc = dispatch_npl<GM_SYM>(kt, A, grid, threads, smem, st); break;
+    case GM_BLOCK: rc = dispatch_npl<GM_BLOCK>(kt, A, grid, threads, smem, st); break;
+    case GM_DENSE: rc = dispatch_npl<GM_DENSE>(kt, A, grid, threads, smem, st); break;
+    default: rc = SLAM_ERR_UNSUPPORTED;
   }
-#undef SLAM_LAUNCH_LBFGS
-  SLAM_CUDA_CHECK(cudaGetLastError());
-  SLAM_CUDA_CHECK(cudaFreeAsync(next, st));
-  SLAM_CUDA_CHECK(cudaFreeAsync(solved, st));
-  return SLAM_OK;
+  cudaFreeAsync(next, st);
+  cudaFreeAsync(solved, st);
+  return rc;
 }

@@ -56,6 +56,9 @@ int lower_const_smush(const SlamTemplateDesc* d, KTemplate* kt, cudaStream_t st)
   (void)d;
   KTemplate tmp = *kt;
   tmp.gmode = GM_SMUSH;
+  int device = 0;
+  SLAM_CUDA_CHECK(cudaGetDevice(&device));
+  if (int rc = keep_async_pool(device)) return rc;
   double* dev = nullptr;
   SLAM_CUDA_CHECK(cudaMallocAsync((void**)&dev, sizeof(double) * 32 * SLAM_MAX_K, st));
   const_smush_kernel<<<1, SLAM_MAX_K, 0, st>>>(tmp, dev);

@@ -1,0 +1,126 @@
+"""Host-side logic that needs no GPU: symbolic circuit, parameter ordering, descriptor lowering, samplers."""
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import BASES, make_pair
+from slam_decomposition_b200 import _lib
+from slam_decomposition_b200.basis import CircuitTemplate
+from slam_decomposition_b200.basisv2 import CircuitTemplateV2
+from slam_decomposition_b200.circuit import Parameter, TemplateCircuit, lower
+from slam_decomposition_b200.distributed import shard_range
+from slam_decomposition_b200.sampler import GateSample, HaarBatchSample, HaarSample
+from slam_decomposition_b200.utils.gates.custom_gates import (ConversionGainGate, ConversionGainSmushGate, CXGate, RiSwapGate,
+                                                             SwapGate)
+
+
+def test_circuit_template_structure_and_param_order():
+    b = CircuitTemplate(maximum_span_guess=4, preseed=False)
+    assert list(b.spanning_range) == [1, 2, 3, 4]
+    for k in (1, 2, 3, 4):
+        b.build(k)
+        orc = O.OracleTemplate("riswap", (0.5,), k=k)
+        assert [p.name for p in b.circuit.parameters] == orc.names_sorted
+        assert b.desc.n_params == 6 * (k + 1) and b.desc.k == k and b.desc.gate_kind == _lib.GATE_RISWAP
+        assert len(b.parameter_guess()) == 6 * (k + 1)
+    # lexicographic order: P0, P1, P10, P11, ...
+    b.build(2)
+    assert [p.name for p in b.circuit.parameters][:4] == ["P0", "P1", "P10", "P11"]
+    # layer 0 qubit 0 holds P0..P2 -> API indices of those names
+    names = [p.name for p in b.circuit.parameters]
+    assert [b.desc.p1q[0][j] for j in range(6)] == [names.index(f"P{j}") for j in range(6)]
+    with pytest.raises(ValueError):
+        b.build(0)
+
+
+def test_no_exterior_and_vz_only_lowering():
+    b = CircuitTemplateV2(base_gates=[RiSwapGate], no_exterior_1q=True, vz_only=True)
+    b.build(3)
+    d = b.desc
+    assert d.vz_only == 1 and d.p1q[0][0] == -1 and d.p1q[3][0] == -1 and d.p1q[1][0] >= 0 and d.p1q[1][1] == -1
+    assert d.n_params == 2 * 2 + 3  # two interior RZ layers + three Q parameters
+    assert all(d.slot_param[g][0] >= 0 for g in range(3))
+
+
+def test_v2_smush_template_parameter_count_matches_reference_formula():
+    """P(k,T) = 6(k-1) + k(2+2T) for the coverage template (parallel_drive_volume.py:175-198)."""
+    for base, T in (("sqiSwap", 2), ("iSwap", 4), ("sqCNOT", 2)):
+        gc, gg, t = BASES[base]
+
+        def pp2(*vargs, gc=gc, gg=gg, t=t, T=T):
+            return ConversionGainSmushGate(vargs[0], vargs[1], gc, gg, vargs[2:2 + T], vargs[2 + T:], t_el=t)
+
+        for k in (1, 3, 6):
+            b = CircuitTemplateV2(n_qubits=2, base_gates=[pp2], no_exterior_1q=1, vz_only=0, param_vec_expand=[2, T, T])
+            b.build(k)
+            assert b.desc.n_params == 6 * (k - 1) + k * (2 + 2 * T)
+            assert b.desc.gate_kind == _lib.GATE_SMUSH and b.desc.T == T and b.desc.n_slots == 5 + 2 * T
+            x = b.parameter_guess()
+            assert len(x) == b.desc.n_params and all(-4 * np.pi <= v <= 4 * np.pi for v in x)
+            assert b.bounds_list is None
+
+
+def test_assign_parameters_and_bound_circuit():
+    b = CircuitTemplate(preseed=False)
+    b.build(1)
+    x = np.arange(12, dtype=float)
+    qc = b.assign_Xk(x)
+    assert qc.num_parameters == 0
+    names = [p.name for p in b.circuit.parameters]
+    first_u = qc[0].operation
+    assert first_u.params == [x[names.index("P0")], x[names.index("P1")], x[names.index("P2")]]
+    desc, names2, numeric = lower(qc)
+    assert names2 == [] and numeric.size == 12 and desc.n_params == 12
+
+
+def test_lower_rejects_unsupported_structures():
+    qc = TemplateCircuit(2)
+    qc.u(Parameter("P0"), Parameter("P1"), Parameter("P2"), 0)
+    with pytest.raises(ValueError):
+        lower(qc)  # no 2Q gate
+    qc.append(RiSwapGate(0.5), (0, 1))
+    qc.append(ConversionGainGate(0, 0, 1, 1, 1), (0, 1))
+    with pytest.raises(NotImplementedError):
+        lower(qc)  # mixed gate families
+    qc3 = TemplateCircuit(3)
+    with pytest.raises(NotImplementedError):
+        lower(qc3)
+    with pytest.raises(NotImplementedError):
+        CircuitTemplate(n_qubits=3)
+    with pytest.raises(NotImplementedError):
+        CircuitTemplate(use_polytopes=True)
+
+
+def test_helpers_pair_is_consistent():
+    desc, orc = make_pair("cg", ("Q", 0.2, np.pi / 4, "Q", 0.5), k=3)
+    assert desc.n_params == orc.n_params == 24 + 6
+    assert desc.slot_param[0][0] >= 0 and desc.slot_param[0][1] == -1 and desc.slot_const[0][1] == 0.2
+
+
+def test_samplers():
+    a, b2 = list(HaarSample(seed=5, n_samples=2))
+    assert np.array_equal(a, b2)  # re-seeded on every call (sampler.py:67-71)
+    assert np.array_equal(a, O.haar_sample_unitary(5))
+    hs = list(HaarBatchSample(seed=1, n_samples=3))
+    assert not np.allclose(hs[0], hs[1])
+    assert np.allclose(list(GateSample(CXGate()))[0], O.CNOT)
+    assert np.allclose(list(GateSample(SwapGate(), n_samples=2))[1], O.SWAP)
+    assert GateSample(SwapGate()).n_qubits == 2
+
+
+def test_gate_costs_follow_the_reference():
+    assert RiSwapGate(0.5).cost() == 0.5
+    g = ConversionGainGate(0, 0, np.pi / 4, np.pi / 4, 1.0)
+    assert g.cost() == pytest.approx(1.0)
+    assert str(g).startswith("2QGate(0.78539816")
+    s = ConversionGainSmushGate(0, 0, np.pi / 2, 0, [1, 2], [3, 4], 0.5)
+    assert s.xy_len == 2 and s.cost() == pytest.approx(0.5) and len(s.params) == 9
+
+
+def test_shard_ranges_partition_exactly():
+    for n in (0, 1, 7, 100000, 10 ** 9):
+        for w in (1, 2, 4, 8):
+            rs = [shard_range(n, r, w) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in rs) - min(b - a for a, b in rs) <= 1
