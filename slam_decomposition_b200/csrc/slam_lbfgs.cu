@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
   const int64_t total = A.Nt * (int64_t)A.restarts;
   // team-uniform scalars
   int state = ST_IDLE, cur = 0, iter = 0, ls = 0, hcount = 0, hpos = 0;
-  int64_t pid = -1;
+  int64_t pid = -1, tgt = 0;
   double f = 0.0, alpha = 1.0, gd = 0.0, gamma = 1.0, f_chk = 0.0;
   bool slow = false;
   unsigned long long evals = 0;
@@ -99,8 +99,13 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
         exhausted = true;
         break;
       }
-      pid = (int64_t)w;
-      const int64_t t = pid / A.restarts;
+      // restart-major order: all targets' restart 0 first, then restart 1, ...  With many more targets than teams
+      // in flight this reproduces the reference's sequential restart loop with its break on first success
+      // (optimizer.py:253-295): restart r of a target is skipped once an earlier restart has solved it.
+      const int64_t r_idx = (int64_t)w / A.Nt;
+      const int64_t t = (int64_t)w - r_idx * A.Nt;
+      pid = t * A.restarts + r_idx;  // index of the (target, restart) pair in the output tables and the x0 stream
+      tgt = t;
       bool skip = A.active && A.active[t] == 0;
       if (!skip && A.early_exit) skip = *((volatile int32_t*)(A.solved + t)) != 0;
       if (skip) {
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
       // restarts still converging towards zero loss run on to f_stop / gtol.
       done = (f < A.f_stop) || (gmax < A.gtol) || (gmax < A.gtol_far && (f > A.f_far || slow)) ||
              (iter >= A.max_iter) || !(f == f);
-      if (!done && A.early_exit && (iter & 3) == 0) done = *((volatile int32_t*)(A.solved + pid / A.restarts)) != 0;
+      if (!done && A.early_exit && (iter & 3) == 0) done = *((volatile int32_t*)(A.solved + tgt)) != 0;
       if (!done) {
         __syncwarp(tmask);  // s_new / y_new / rho visible to the team
         // two-loop recursion on the register slice: q <- H g
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
       if (sub == 0) {
         A.out_loss[pid] = f;
         A.out_iters[pid] = iter;
-        if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + pid / A.restarts, 1);
+        if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + tgt, 1);
       }
       for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = xf[j];
       state = ST_IDLE;
