@@ -216,10 +216,15 @@ def run_ours(args):
         # the only inter-GPU step: gather of the per-target result table
         return D.allgather_table({"loss": res_loss, "k": res_k, "x": res_x})
 
+    gather_ms = []
+
     def step_resident():
         res = opt._run_batch(V_dev, k_range)
-        tab = gather(torch.as_tensor(res["best_loss"], device=dev), torch.as_tensor(res["best_k"], device=dev),
-                     res["best_x"])
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        tab = gather(res["best_loss_dev"], res["best_k_dev"], res["best_x"])
+        g1.record()
+        gather_ms.append((g0, g1))
         return res, tab
 
     # ---- warm-up ------------------------------------------------------------------------------------
@@ -234,6 +239,7 @@ def run_ours(args):
         clocks.start()
     engine.LBFGS_EVENTS = []
     opt.launch_evals = []
+    gather_ms.clear()
     launches0 = engine.LAUNCHES
     evals_total = 0
     solved = 0
@@ -288,6 +294,7 @@ def run_ours(args):
     e2e_all = D.sum_over_ranks(float(e2e_evals), dev)
 
     if rank != 0:
+        D.shutdown()
         return 0
 
     # ---- rank 0: denominators, micro-benchmarks, CPU baseline, the JSON line ---------------------------
@@ -301,6 +308,7 @@ def run_ours(args):
                 "ms_per_step": 1e3 * t_e2e / args.steps,
                 "haar_decompositions_per_sec": world * Nt * args.steps / t_e2e},
         "gpu_launches": launches,
+        "collective_ms_per_step": sum(a.elapsed_time(b) for a, b in gather_ms[: args.steps]) / args.steps,
         "haar_decompositions_per_sec": world * Nt * args.steps / t,
         "solved_fraction": solved_all / (world * Nt * args.steps),
         "evals_per_step": evals_all / args.steps,
@@ -327,6 +335,7 @@ def run_ours(args):
                        f"sqCNOT templates cycling k=1..{K_MAX}; one loss+grad evaluation = (P+1) numpy template evaluations"),
             "raw_template_evals_per_s": s["template_evals_per_s"], "restarts_completed": s["restarts"]}
     print(json.dumps(line), flush=True)
+    D.shutdown()
     return 0
 
 

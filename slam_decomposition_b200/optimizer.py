@@ -177,7 +177,7 @@ class TemplateOptimizer:
                 break
         self.last_stats = {"evals": int(evals.item())}
         return {"best_loss": best_loss.cpu().numpy(), "best_k": best_k.cpu().numpy(), "best_P": best_P.cpu().numpy(),
-                "best_x": best_x, "per_k": per_k}
+                "best_x": best_x, "per_k": per_k, "best_loss_dev": best_loss, "best_k_dev": best_k}
 
     def approximate_targets(self, targets, k_range: Optional[Sequence[int]] = None, opts=None) -> dict:
         """Host-buffer batch API: ``targets`` complex128 [Nt,4,4] (numpy, or a pinned/CPU torch tensor) ->

@@ -116,3 +116,22 @@ def test_trajectory_matches_iterate_time():
                         for b in range(B)])
     assert np.mean(np.abs(c8.cpu().numpy() - ref_all) < 1e-12) > 0.97
     assert np.abs(c8.cpu().numpy() - ref_all).max() <= 1.0000001e-8
+
+
+def test_parallel_driven_gate_widget_matches_reference_semantics():
+    from slam_decomposition_b200.utils.pd_playground import ParallelDrivenGateWidget, trajectories
+
+    w = ParallelDrivenGateWidget(N=10, gc=np.pi / 2, gg=0)
+    w.prepare_parameters_nonuniform([3] * w.N, [0] * w.N)  # ImprovedCX (pd_playground.py:255-258)
+    w.iterate_time(R=5)
+    ref_c, ref_U = O.trajectory((0, 0, 0, 0), np.pi / 2, 0, 0, 0, [3] * 10, [0] * 10, 0.1, 5)
+    got = np.array(w.coordinate_list)
+    assert got.shape == (10, 5, 3) and np.abs(got - ref_c).max() <= 1.0000001e-8
+    assert np.abs(w.final_unitary - ref_U).max() < TOL_U
+    assert np.abs(w.solve_end() - ref_U).max() < TOL_U
+    assert w.end_segment_list[-1] == w.coordinate_list[-1][-1]
+    # default widget (no 1Q drive): after 10 x 0.1 of an iSWAP-strength drive the gate is iSWAP
+    w0 = ParallelDrivenGateWidget()
+    assert np.allclose(O.c1c2c3(w0.solve_end()), (0.5, 0.5, 0.0), atol=1e-8)
+    c, U = trajectories(np.zeros((3, 8)), np.ones((3, 4)), np.ones((3, 4)))
+    assert c.shape == (3, 4, 5, 3) and U.shape == (3, 4, 4)
