@@ -15,7 +15,9 @@ GATE_RISWAP, GATE_CG, GATE_SMUSH, GATE_SMUSH_1QPHASE, GATE_FIXED = range(5)
 COST_BASIC, COST_SQUARE, COST_BASIC_INVERSE = range(3)
 WEYL_FOLD, WEYL_ROUND8 = 1, 2
 
-LIB_PATH = Path(__file__).resolve().parent / "libslam_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("SLAM_B200_LIB") or (Path(__file__).resolve().parent / "libslam_b200.so"))
 
 
 class SlamTemplateDesc(C.Structure):

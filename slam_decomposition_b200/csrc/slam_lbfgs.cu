@@ -14,6 +14,7 @@
 // its slice of the two-loop working vector in registers, so the recursion is a stream of independent
 // shared-memory loads and FMAs with one 2-stage shuffle reduction per history pair.
 #include <cfloat>
+#include <cstdlib>
 
 #include "slam_host.h"
 #include "slam_philox.cuh"
@@ -23,6 +24,10 @@ namespace slam {
 constexpr int LPP = 4;
 constexpr int kMaxHist = 8;
 constexpr double kArmijo = 1e-4;
+#ifndef SLAM_LBFGS_MAX_THREADS
+#define SLAM_LBFGS_MAX_THREADS 384  // register cap 168/thread -> up to 12 warps per SM
+#endif
+constexpr int kLbfgsMaxThreads = SLAM_LBFGS_MAX_THREADS;
 
 struct LbfgsArgs {
   const double* V;
@@ -59,23 +64,33 @@ __device__ __forceinline__ double tmax(double v, unsigned mask) {
 
 enum { ST_IDLE = 0, ST_INIT = 1, ST_LS = 2 };
 
-// NPL = vector entries per lane held in registers (P <= 4 * NPL)
-template <int GM, int NPL>
-__global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ KTemplate kt,
-                                                       const __grid_constant__ LbfgsArgs A) {
+// NPL = max vector entries per lane held in registers (Pp <= 4 * NPL); HT = storage type of the (s, y) history.
+//
+// Shared-memory slice of a team (doubles): [x0 | g0 | x1 | g1] 4 Pp, history S, Y (2 m Pp elements of HT),
+// rho[m], alp[m], (cos, sin) cache.  Vectors are padded to Pp = 4 ceil(P/4) entries that stay zero, so every lane owns
+// exactly npl = Pp/4 entries (j = sub + 4 i) and the vector loops need no per-lane bounds checks.
+// The search direction is not stored: while a line search is in progress it is (xt - x) / alpha.
+template <int GM, int NPL, typename HT>
+__global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid_constant__ KTemplate kt,
+                                                                    const __grid_constant__ LbfgsArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int P = kt.P, m = A.m;
+  const int Pp = (P + 3) & ~3;
+  const int npl = Pp >> 2;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int team = tid >> 2, sub = tid & 3;
   const unsigned tmask = 0xFu << (lane & ~3);
   double* base = smem + (size_t)team * A.RS;
-  // two (x, g) buffers: buffer b holds x at base + 2bP and g at base + (2b+1)P
-  double* D = base + 4 * P;
-  double* S = base + 5 * P;
-  double* Y = S + m * P;
-  double* rho = Y + m * P;
-  double2* tg = reinterpret_cast<double2*>(rho + m + ((5 * P + m) & 1));
+  HT* S = reinterpret_cast<HT*>(base + 4 * Pp);
+  HT* Y = S + m * Pp;
+  double* rho = base + 4 * Pp + (2 * m * Pp * (int)sizeof(HT)) / 8;
+  double* alp = rho + m;
+  double2* tg = reinterpret_cast<double2*>(alp + m);
+
+  // zero the slice once: the padding entries of every vector must stay zero
+  for (int j = sub; j < A.RS; j += LPP) base[j] = 0.0;
+  __syncwarp();
 
   const int64_t total = A.Nt * (int64_t)A.restarts;
   // team-uniform scalars
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
       }
       // initial point into the trial buffer (buffer 1), target columns into registers
       cur = 0;
-      double* xt = base + 2 * P;
+      double* xt = base + 2 * Pp;
       for (int j = sub; j < P; j += LPP)
         xt[j] = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
 #pragma unroll
@@ -138,38 +153,38 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
     __syncwarp();
 
     // ---------------- one loss+grad evaluation per team (convergent) -----------------------------
-    double* xt = base + 2 * (cur ^ 1) * P;
-    double* gt = xt + P;
+    double* xt = base + 2 * (cur ^ 1) * Pp;
+    double* gt = xt + Pp;
     const double ft = loss_grad_team<LPP, GM, true>(kt, xt, tg, gt, vcol, A.cost_kind, sub, nullptr);
     if (state == ST_IDLE) continue;
     ++evals;
 
     // ---------------- per-team bookkeeping (divergent across teams) ------------------------------
-    const double* x = base + 2 * cur * P;
-    const double* g = x + P;
+    const double* x = base + 2 * cur * Pp;
+    const double* g = x + Pp;
     const bool first = (state == ST_INIT);
     const bool accepted = first || (ft <= f + kArmijo * alpha * gd);  // Armijo; NaN compares false
     bool done = false;
-    double q[NPL];  // this lane's slice of the working vector (entries j = sub + 4 i)
     if (accepted) {
-      // history pair s = xt - x, y = gt - g into slot hpos; q <- gt
-      double* s_new = S + hpos * P;
-      double* y_new = Y + hpos * P;
+      double q[NPL];  // this lane's slice of the working vector (entries j = sub + 4 i)
+      // history pair s = xt - x, y = gt - g into slot hpos (rounded to HT; the curvature uses the rounded values); q <- gt
+      HT* s_new = S + hpos * Pp;
+      HT* y_new = Y + hpos * Pp;
       double sy = 0.0, yy = 0.0, gmax = 0.0;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
-        const int j = sub + LPP * i;
         q[i] = 0.0;
-        if (j < P) {
+        if (i < npl) {
+          const int j = sub + LPP * i;
           const double gj = gt[j];
           q[i] = gj;
           gmax = fmax(gmax, fabs(gj));
           if (!first) {
-            const double sj = xt[j] - x[j], yj = gj - g[j];
-            s_new[j] = sj;
-            y_new[j] = yj;
-            sy = fma(sj, yj, sy);
-            yy = fma(yj, yj, yy);
+            const HT sf = (HT)(xt[j] - x[j]), yf = (HT)(gj - g[j]);
+            s_new[j] = sf;
+            y_new[j] = yf;
+            sy = fma((double)sf, (double)yf, sy);
+            yy = fma((double)yf, (double)yf, yy);
           }
         }
       }
@@ -203,76 +218,59 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
       if (!done) {
         __syncwarp(tmask);  // s_new / y_new / rho visible to the team
         // two-loop recursion on the register slice: q <- H g
-        double al[kMaxHist];
+        for (int h = 0; h < hcount; ++h) {
+          int slot = hpos - 1 - h;
+          if (slot < 0) slot += m;
+          const HT* s = S + slot * Pp + sub;
+          const HT* y = Y + slot * Pp + sub;
+          double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-        for (int h = 0; h < kMaxHist; ++h) {
-          al[h] = 0.0;
-          if (h < hcount) {
-            int slot = hpos - 1 - h;
-            if (slot < 0) slot += m;
-            const double* s = S + slot * P;
-            const double* y = Y + slot * P;
-            double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-            for (int i = 0; i < NPL; i += 2) {
-              const int j0 = sub + LPP * i, j1 = j0 + LPP;
-              if (j0 < P) a0 = fma(s[j0], q[i], a0);
-              if (i + 1 < NPL && j1 < P) a1 = fma(s[j1], q[i + 1], a1);
-            }
-            const double a = tsum(a0 + a1, tmask) * rho[slot];
-            al[h] = a;
-#pragma unroll
-            for (int i = 0; i < NPL; ++i) {
-              const int j = sub + LPP * i;
-              if (j < P) q[i] = fma(-a, y[j], q[i]);
-            }
+          for (int i = 0; i < NPL; i += 2) {
+            if (i < npl) a0 = fma((double)s[LPP * i], q[i], a0);
+            if (i + 1 < NPL && i + 1 < npl) a1 = fma((double)s[LPP * (i + 1)], q[i + 1], a1);
           }
+          const double a = tsum(a0 + a1, tmask) * rho[slot];
+          if (sub == 0) alp[slot] = a;
+#pragma unroll
+          for (int i = 0; i < NPL; ++i)
+            if (i < npl) q[i] = fma(-a, (double)y[LPP * i], q[i]);
         }
+        __syncwarp(tmask);
 #pragma unroll
         for (int i = 0; i < NPL; ++i) q[i] *= gamma;
+        for (int h = hcount - 1; h >= 0; --h) {
+          int slot = hpos - 1 - h;
+          if (slot < 0) slot += m;
+          const HT* s = S + slot * Pp + sub;
+          const HT* y = Y + slot * Pp + sub;
+          double b0 = 0.0, b1 = 0.0;
 #pragma unroll
-        for (int h = kMaxHist - 1; h >= 0; --h) {
-          if (h < hcount) {
-            int slot = hpos - 1 - h;
-            if (slot < 0) slot += m;
-            const double* s = S + slot * P;
-            const double* y = Y + slot * P;
-            double b0 = 0.0, b1 = 0.0;
-#pragma unroll
-            for (int i = 0; i < NPL; i += 2) {
-              const int j0 = sub + LPP * i, j1 = j0 + LPP;
-              if (j0 < P) b0 = fma(y[j0], q[i], b0);
-              if (i + 1 < NPL && j1 < P) b1 = fma(y[j1], q[i + 1], b1);
-            }
-            const double c = al[h] - tsum(b0 + b1, tmask) * rho[slot];
-#pragma unroll
-            for (int i = 0; i < NPL; ++i) {
-              const int j = sub + LPP * i;
-              if (j < P) q[i] = fma(c, s[j], q[i]);
-            }
+          for (int i = 0; i < NPL; i += 2) {
+            if (i < npl) b0 = fma((double)y[LPP * i], q[i], b0);
+            if (i + 1 < NPL && i + 1 < npl) b1 = fma((double)y[LPP * (i + 1)], q[i + 1], b1);
           }
+          const double c = alp[slot] - tsum(b0 + b1, tmask) * rho[slot];
+#pragma unroll
+          for (int i = 0; i < NPL; ++i)
+            if (i < npl) q[i] = fma(c, (double)s[LPP * i], q[i]);
         }
         // d = -q ; gd = g.d ; gg = g.g  (g = gt: the accepted gradient)
         double gdn = 0.0, gg = 0.0;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const int j = sub + LPP * i;
-          if (j < P) {
-            const double gj = gt[j];
+        for (int i = 0; i < NPL; ++i)
+          if (i < npl) {
+            const double gj = gt[sub + LPP * i];
             q[i] = -q[i];
             gdn = fma(gj, q[i], gdn);
             gg = fma(gj, gj, gg);
           }
-        }
         gdn = tsum(gdn, tmask);
         gg = tsum(gg, tmask);
         if (hcount == 0 || !(gdn < 0.0)) {  // first step or not a descent direction: steepest descent, unit length
           hcount = 0;
 #pragma unroll
-          for (int i = 0; i < NPL; ++i) {
-            const int j = sub + LPP * i;
-            if (j < P) q[i] = -gt[j];
-          }
+          for (int i = 0; i < NPL; ++i)
+            if (i < npl) q[i] = -gt[sub + LPP * i];
           gdn = -gg;
           alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
         } else {
@@ -281,30 +279,27 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
         gd = gdn;
         ls = 0;
         state = ST_LS;
-        // store the direction and the next trial point x_new = xt + alpha d (into the old current buffer)
-        double* xn = base + 2 * (cur ^ 1) * P;
+        // next trial point x_new = xt + alpha d, into the old current buffer
+        double* xn = base + 2 * (cur ^ 1) * Pp;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const int j = sub + LPP * i;
-          if (j < P) {
-            D[j] = q[i];
-            xn[j] = fma(alpha, q[i], xt[j]);
-          }
-        }
+        for (int i = 0; i < NPL; ++i)
+          if (i < npl) xn[sub + LPP * i] = fma(alpha, q[i], xt[sub + LPP * i]);
       }
     } else {
-      // backtrack with the cubic through (0, f, gd) and (alpha, ft, gdt), safeguarded to [0.1, 0.5] alpha
+      // backtrack with the cubic through (0, f, gd) and (alpha, ft, gdt), safeguarded to [0.1, 0.5] alpha;
+      // the direction is recovered from the failed trial point: d = (xt - x) / alpha
+      double dx[NPL];
       double gdt = 0.0;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
-        const int j = sub + LPP * i;
-        q[i] = 0.0;
-        if (j < P) {
-          q[i] = D[j];
-          gdt = fma(gt[j], q[i], gdt);
+        dx[i] = 0.0;
+        if (i < npl) {
+          const int j = sub + LPP * i;
+          dx[i] = xt[j] - x[j];
+          gdt = fma(gt[j], dx[i], gdt);
         }
       }
-      gdt = tsum(gdt, tmask);
+      gdt = tsum(gdt, tmask) / alpha;
       double an = 0.5 * alpha;
       if (ft == ft && gdt == gdt) {
         const double d1 = gd + gdt - 3.0 * (ft - f) / alpha;
@@ -318,41 +313,41 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
           }
         }
       }
-      alpha = fmin(fmax(an, 0.1 * alpha), 0.5 * alpha);
+      an = fmin(fmax(an, 0.1 * alpha), 0.5 * alpha);
+      double ratio = an / alpha;
+      alpha = an;
       ++ls;
+      bool reset = false;
       if (ls > 30) {
         if (hcount > 0) {  // curvature model is bad: restart from steepest descent
           hcount = 0;
           double gg = 0.0;
 #pragma unroll
-          for (int i = 0; i < NPL; ++i) {
-            const int j = sub + LPP * i;
-            if (j < P) {
-              const double gj = g[j];
-              q[i] = -gj;
-              D[j] = -gj;
+          for (int i = 0; i < NPL; ++i)
+            if (i < npl) {
+              const double gj = g[sub + LPP * i];
+              dx[i] = -gj;
               gg = fma(gj, gj, gg);
             }
-          }
           gg = tsum(gg, tmask);
           gd = -gg;
           alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+          ratio = alpha;
           ls = 0;
+          reset = true;
         } else {
           done = true;  // no progress possible at working precision
         }
       }
+      (void)reset;
       if (!done) {
-        double* xn = base + 2 * (cur ^ 1) * P;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const int j = sub + LPP * i;
-          if (j < P) xn[j] = fma(alpha, q[i], x[j]);
-        }
+        for (int i = 0; i < NPL; ++i)
+          if (i < npl) xt[sub + LPP * i] = fma(ratio, dx[i], x[sub + LPP * i]);
       }
     }
     if (done) {
-      const double* xf = base + 2 * cur * P;
+      const double* xf = base + 2 * cur * Pp;
       if (sub == 0) {
         A.out_loss[pid] = f;
         A.out_iters[pid] = iter;
@@ -365,27 +360,39 @@ __global__ void __launch_bounds__(256, 1) lbfgs_kernel(const __grid_constant__ K
   if (A.out_evals && sub == 0 && evals) atomicAdd(A.out_evals, evals);
 }
 
-static int team_doubles(const KTemplate& kt, int m) {
-  int rs = (5 + 2 * m) * kt.P + m + ((5 * kt.P + m) & 1) + 2 * kt.n_trig;
+static int team_doubles(const KTemplate& kt, int m, int hist_bytes) {
+  const int Pp = (kt.P + 3) & ~3;
+  int rs = 4 * Pp + (2 * m * Pp * hist_bytes) / 8 + 2 * m + 2 * kt.n_trig;
   while ((rs & 15) != 4) ++rs;  // 4 (mod 16): the 4 teams of a half-warp hit disjoint bank groups
   return rs;
 }
 
-template <int GM, int NPL>
+template <int GM, int NPL, typename HT>
 static int launch_lbfgs(const KTemplate& kt, const LbfgsArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
-  auto kern = lbfgs_kernel<GM, NPL>;
+  auto kern = lbfgs_kernel<GM, NPL, HT>;
   SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, threads, smem, st>>>(kt, A);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }
 
-template <int GM>
+template <int GM, typename HT>
 static int dispatch_npl(const KTemplate& kt, const LbfgsArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
-  if (kt.P <= 32) return launch_lbfgs<GM, 8>(kt, A, grid, threads, smem, st);
-  if (kt.P <= 56) return launch_lbfgs<GM, 14>(kt, A, grid, threads, smem, st);
-  if (kt.P <= 96) return launch_lbfgs<GM, 24>(kt, A, grid, threads, smem, st);
+  const int Pp = (kt.P + 3) & ~3;
+  if (Pp <= 32) return launch_lbfgs<GM, 8, HT>(kt, A, grid, threads, smem, st);
+  if (Pp <= 56) return launch_lbfgs<GM, 14, HT>(kt, A, grid, threads, smem, st);
+  if (Pp <= 96) return launch_lbfgs<GM, 24, HT>(kt, A, grid, threads, smem, st);
   return SLAM_ERR_UNSUPPORTED;  // the device optimiser keeps 4*NPL <= 96 parameters in registers
+}
+
+template <typename HT>
+static int dispatch_gm(const KTemplate& kt, const LbfgsArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
+  switch (kt.gmode) {
+    case GM_SYM: return dispatch_npl<GM_SYM, HT>(kt, A, grid, threads, smem, st);
+    case GM_BLOCK: return dispatch_npl<GM_BLOCK, HT>(kt, A, grid, threads, smem, st);
+    case GM_DENSE: return dispatch_npl<GM_DENSE, HT>(kt, A, grid, threads, smem, st);
+    default: return SLAM_ERR_UNSUPPORTED;
+  }
 }
 
 }  // namespace slam
@@ -430,13 +437,20 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   SLAM_CUDA_CHECK(cudaGetDevice(&dev));
   SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // history storage: float by default (halves the dominant shared-memory consumer -> 1.5x the resident teams; the
+  // curvature scalars are computed from the rounded pairs, so the two-loop recursion stays self-consistent);
+  // SLAM_B200_HIST_F64=1 keeps the pairs in double for A/B comparisons.
+  const char* henv = getenv("SLAM_B200_HIST_F64");
+  const bool hist64 = henv && henv[0] == '1';
+  const int hb = hist64 ? 8 : 4;
   // history length and teams per CTA from the shared-memory budget (one persistent CTA per SM)
+  const int max_teams = kLbfgsMaxThreads / LPP;
   int m = opts->history ? opts->history : 6;
-  int teams = 64;
-  if (!opts->history)
-    while (m > 4 && (size_t)team_doubles(kt, m) * 8 * 64 > (size_t)max_smem) --m;
-  while (teams > 8 && (size_t)team_doubles(kt, m) * 8 * teams > (size_t)max_smem) teams -= 8;
-  const int RS = team_doubles(kt, m);
+  int teams = max_teams;
+  if (!opts->history)  // prefer a full complement of teams (occupancy) over a longer history, down to m = 4
+    while (m > 4 && (size_t)team_doubles(kt, m, hb) * 8 * max_teams > (size_t)max_smem) --m;
+  while (teams > 8 && (size_t)team_doubles(kt, m, hb) * 8 * teams > (size_t)max_smem) teams -= 8;
+  const int RS = team_doubles(kt, m, hb);
   const size_t smem = (size_t)RS * 8 * teams;
   if (smem > (size_t)max_smem) return SLAM_ERR_UNSUPPORTED;
 
@@ -461,12 +475,7 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   const int64_t total = Nt * (int64_t)restarts;
   const int grid = (int)std::min<int64_t>((int64_t)sms, (total + teams - 1) / teams);
   const int threads = teams * LPP;
-  switch (kt.gmode) {
-    case GM_SYM: rc = dispatch_npl<GM_SYM>(kt, A, grid, threads, smem, st); break;
-    case GM_BLOCK: rc = dispatch_npl<GM_BLOCK>(kt, A, grid, threads, smem, st); break;
-    case GM_DENSE: rc = dispatch_npl<GM_DENSE>(kt, A, grid, threads, smem, st); break;
-    default: rc = SLAM_ERR_UNSUPPORTED;
-  }
+  rc = hist64 ? dispatch_gm<double>(kt, A, grid, threads, smem, st) : dispatch_gm<float>(kt, A, grid, threads, smem, st);
   cudaFreeAsync(next, st);
   cudaFreeAsync(solved, st);
   return rc;
