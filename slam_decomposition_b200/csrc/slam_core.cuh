@@ -401,15 +401,16 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
       for (int e = 0; e < 4; ++e) EA[e] = EB[e] = mkc(0.0, 0.0);
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
-        apply1q<1, OP_H>(r[c], A);  // r <- L_i^dagger r : columns of R_i
-        apply1q<0, OP_H>(r[c], B);
+        // un-peel in two steps: r holds rho = (A (x) B) r_i, so (A^dagger (x) I) rho = (I (x) B) r_i is exactly the
+        // vector v needed by the A-environment; the second step then gives r_i (columns of R_i)
+        apply1q<1, OP_H>(r[c], A);
         cd v[4], u[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           v[a] = r[c][a];
           u[a] = w[c][a];
         }
-        apply1q<0, OP_N>(v, B);  // v = (I (x) B) r
+        apply1q<0, OP_H>(r[c], B);
         apply1q<1, OP_T>(u, A);  // u = w (A (x) I)
         // EA[a][a'] = sum_b w[(a,b)] v[(a',b)] ; EB[b][b'] = sum_a' u[(a',b)] r[(a',b')]
 #pragma unroll

@@ -38,7 +38,8 @@ struct LbfgsArgs {
   int64_t Nt;
   int restarts;
   int m;        // history length
-  int RS;       // doubles of shared memory per team
+  int RS;       // doubles of shared memory per team (vectors, rho, alp, trig cache)
+  int HS;       // history elements (of HT) per team; the history slices follow the RS slices of all teams
   int max_iter;
   int cost_kind;
   int early_exit;
@@ -66,8 +67,8 @@ enum { ST_IDLE = 0, ST_INIT = 1, ST_LS = 2 };
 
 // NPL = max vector entries per lane held in registers (Pp <= 4 * NPL); HT = storage type of the (s, y) history.
 //
-// Shared-memory slice of a team (doubles): [x0 | g0 | x1 | g1] 4 Pp, history S, Y (2 m Pp elements of HT),
-// rho[m], alp[m], (cos, sin) cache.  Vectors are padded to Pp = 4 ceil(P/4) entries that stay zero, so every lane owns
+// Shared-memory slice of a team (doubles): [x0 | g0 | x1 | g1] 4 Pp, rho[m], alp[m], (cos, sin) cache; the history
+// S, Y (2 m Pp elements of HT per team) is a second region behind the slices of all teams.  Vectors are padded to Pp = 4 ceil(P/4) entries that stay zero, so every lane owns
 // exactly npl = Pp/4 entries (j = sub + 4 i) and the vector loops need no per-lane bounds checks.
 // The search direction is not stored: while a line search is in progress it is (xt - x) / alpha.
 template <int GM, int NPL, typename HT>
@@ -82,14 +83,16 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
   const int team = tid >> 2, sub = tid & 3;
   const unsigned tmask = 0xFu << (lane & ~3);
   double* base = smem + (size_t)team * A.RS;
-  HT* S = reinterpret_cast<HT*>(base + 4 * Pp);
+  // history slices live in their own region with a stride that tiles the 32 banks for HT-sized accesses
+  HT* S = reinterpret_cast<HT*>(smem + (size_t)(blockDim.x / LPP) * A.RS) + (size_t)team * A.HS;
   HT* Y = S + m * Pp;
-  double* rho = base + 4 * Pp + (2 * m * Pp * (int)sizeof(HT)) / 8;
+  double* rho = base + 4 * Pp;
   double* alp = rho + m;
   double2* tg = reinterpret_cast<double2*>(alp + m);
 
   // zero the slice once: the padding entries of every vector must stay zero
   for (int j = sub; j < A.RS; j += LPP) base[j] = 0.0;
+  for (int j = sub; j < A.HS; j += LPP) S[j] = (HT)0;
   __syncwarp();
 
   const int64_t total = A.Nt * (int64_t)A.restarts;
@@ -360,11 +363,23 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
   if (A.out_evals && sub == 0 && evals) atomicAdd(A.out_evals, evals);
 }
 
-static int team_doubles(const KTemplate& kt, int m, int hist_bytes) {
+static int team_doubles(const KTemplate& kt, int m) {
   const int Pp = (kt.P + 3) & ~3;
-  int rs = 4 * Pp + (2 * m * Pp * hist_bytes) / 8 + 2 * m + 2 * kt.n_trig;
-  while ((rs & 15) != 4) ++rs;  // 4 (mod 16): the 4 teams of a half-warp hit disjoint bank groups
+  int rs = 4 * Pp + 2 * m + 2 * kt.n_trig;
+  while ((rs & 15) != 4) ++rs;  // 32 B (mod 128 B): the 4 teams of a half-warp hit disjoint banks on 64-bit accesses
   return rs;
+}
+
+static int team_hist_elems(const KTemplate& kt, int m, int hist_bytes) {
+  const int Pp = (kt.P + 3) & ~3;
+  int hs = 2 * m * Pp;
+  // stride = 4 elements (mod 128 B): 8 teams x 16 B (float) or 4 teams x 32 B (double) tile the 32 banks
+  while ((hs * hist_bytes) % 128 != 4 * hist_bytes) ++hs;
+  return hs;
+}
+
+static size_t team_bytes(const KTemplate& kt, int m, int hist_bytes) {
+  return (size_t)team_doubles(kt, m) * 8 + (size_t)team_hist_elems(kt, m, hist_bytes) * hist_bytes;
 }
 
 template <int GM, int NPL, typename HT>
@@ -448,10 +463,11 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   int m = opts->history ? opts->history : 6;
   int teams = max_teams;
   if (!opts->history)  // prefer a full complement of teams (occupancy) over a longer history, down to m = 4
-    while (m > 4 && (size_t)team_doubles(kt, m, hb) * 8 * max_teams > (size_t)max_smem) --m;
-  while (teams > 8 && (size_t)team_doubles(kt, m, hb) * 8 * teams > (size_t)max_smem) teams -= 8;
-  const int RS = team_doubles(kt, m, hb);
-  const size_t smem = (size_t)RS * 8 * teams;
+    while (m > 4 && team_bytes(kt, m, hb) * max_teams > (size_t)max_smem) --m;
+  while (teams > 8 && team_bytes(kt, m, hb) * teams > (size_t)max_smem) teams -= 8;
+  const int RS = team_doubles(kt, m);
+  const int HS = team_hist_elems(kt, m, hb);
+  const size_t smem = team_bytes(kt, m, hb) * teams;
   if (smem > (size_t)max_smem) return SLAM_ERR_UNSUPPORTED;
 
   // stream-ordered scratch: work counter + per-target early-exit flags
@@ -466,7 +482,7 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
 
   LbfgsArgs A;
   A.V = V; A.x0 = x0; A.ldx0 = ldx0; A.seed = seed; A.active = active; A.Nt = Nt; A.restarts = restarts;
-  A.m = m; A.RS = RS; A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit;
+  A.m = m; A.RS = RS; A.HS = HS; A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit;
   A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
