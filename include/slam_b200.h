@@ -142,6 +142,14 @@ typedef struct SlamOptOpts {
   double gtol_far;       /* ... or max|g| < gtol_far while loss > f_far (a non-zero local min)   */
   double f_far;
   double x0_lo, x0_hi;   /* when x0 == NULL: x0 ~ U[x0_lo, x0_hi) from Philox(seed)              */
+  /* optional per-iteration trace (replaces callbackF, optimizer.py:217-224): after accepted iteration i (1-based,
+     i <= trace_cap) of problem p = target*restarts + restart the kernel stores the loss in
+     trace_loss[p*trace_cap + i-1] and the parameters in trace_x[(p*trace_cap + i-1)*P ...]; out_iters gives the
+     number of iterations.  [dev] pointers, NULL / 0 = off.                                                      */
+  int32_t trace_cap;
+  int32_t reserved;
+  double* trace_loss;
+  double* trace_x;
 } SlamOptOpts;
 
 void slam_opt_defaults(SlamOptOpts* o);

@@ -50,6 +50,10 @@ class SlamOptOpts(C.Structure):
         ("f_far", C.c_double),
         ("x0_lo", C.c_double),
         ("x0_hi", C.c_double),
+        ("trace_cap", C.c_int32),
+        ("reserved", C.c_int32),
+        ("trace_loss", C.c_void_p),
+        ("trace_x", C.c_void_p),
     ]
 
 

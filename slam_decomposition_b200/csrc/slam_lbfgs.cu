@@ -44,6 +44,9 @@ struct LbfgsArgs {
   int cost_kind;
   int early_exit;
   double success_threshold, f_stop, gtol, gtol_far, f_far, x0_lo, x0_span;
+  int trace_cap;
+  double* trace_loss;
+  double* trace_x;
   double* out_loss;
   double* out_x;
   int32_t* out_iters;
@@ -204,6 +207,12 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
           hcount = m - 1;  // the rejected pair overwrote the oldest slot
         }
         ++iter;
+        if (iter <= A.trace_cap) {  // per-iteration trace (the reference's callbackF)
+          const int64_t e = pid * A.trace_cap + (iter - 1);
+          if (sub == 0) A.trace_loss[e] = ft;
+          if (A.trace_x)
+            for (int j = sub; j < P; j += LPP) A.trace_x[e * P + j] = xt[j];
+        }
       }
       cur ^= 1;  // trial point becomes the current point
       f = ft;
@@ -427,6 +436,10 @@ extern "C" void slam_opt_defaults(SlamOptOpts* o) {
   o->f_far = 1e-6;
   o->x0_lo = 0.0;                // basis.py:111: np.random.random(P) * 2 pi
   o->x0_hi = 6.283185307179586;
+  o->trace_cap = 0;
+  o->reserved = 0;
+  o->trace_loss = nullptr;
+  o->trace_x = nullptr;
 }
 
 extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
@@ -485,6 +498,8 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   A.m = m; A.RS = RS; A.HS = HS; A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit;
   A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
+  A.trace_cap = (opts->trace_loss && opts->trace_cap > 0) ? opts->trace_cap : 0;
+  A.trace_loss = opts->trace_loss; A.trace_x = opts->trace_x;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved;
 

@@ -147,6 +147,15 @@ class TemplateOptimizer:
             x0, lo, hi = self._x0(Nt, device)
             opts.x0_lo, opts.x0_hi = lo, hi
             seed = int(np.random.randint(0, 2 ** 62))
+            trace_loss = trace_x = None
+            if keep_history:
+                # per-iteration trace buffers (bounded: ~256 MiB); iterations beyond the cap are not recorded
+                cap = int(max(8, min(opts.max_iter, (1 << 28) // max(1, Nt * R * (P + 1) * 8))))
+                trace_loss = torch.zeros((Nt * R, cap), dtype=torch.float64, device=device)
+                trace_x = torch.zeros((Nt * R, cap, P), dtype=torch.float64, device=device)
+                opts.trace_cap, opts.trace_loss, opts.trace_x = cap, trace_loss.data_ptr(), trace_x.data_ptr()
+            else:
+                opts.trace_cap, opts.trace_loss, opts.trace_x = 0, None, None
             ev_before = int(evals.item()) if timing else 0
             loss, x, iters = engine.lbfgs_solve(desc, V, R, opts, x0=x0, seed=seed, active=active, evals=evals,
                                                 out=(ws["loss"], x, ws["iters"]))
@@ -168,7 +177,7 @@ class TemplateOptimizer:
             best_P = torch.where(improved, torch.full_like(best_P, P), best_P)
             if keep_history:  # per-restart tables are only copied out when the caller wants histories
                 per_k.append({"k": k, "loss": loss.clone(), "x": x.clone(), "iters": iters.clone(),
-                              "active": active.clone(), "desc": desc})
+                              "active": active.clone(), "desc": desc, "trace_loss": trace_loss, "trace_x": trace_x})
             active = ((active != 0) & ~(best_loss < self.success_threshold)).to(torch.int32)
             n_left = int(active.sum().item())
             logging.info(f"Cycle (k ={k}), solved {Nt - n_left}/{Nt}")
@@ -224,21 +233,30 @@ class TemplateOptimizer:
             if self.use_callback:
                 if success or self.override_fail:
                     tl: list = []
-                    last = None
+                    coords: list = []
                     for rec in res["per_k"]:
                         if int(rec["active"][i].item()) == 0:
                             continue
-                        li = rec["loss"][i]
                         tl.extend([-1, rec["k"]])
-                        tl.extend(float(v) for v in li.tolist() if v < 1e300)
-                        last = rec
-                    self.training_loss.append(tl)
-                    coords = []
-                    if last is not None:
-                        keep = last["loss"][i] < 1e300
-                        if bool(keep.any()):
-                            U = engine.template_eval(last["desc"], last["x"][i][keep].contiguous())
+                        coords = []  # coordinate_list is reset per k (optimizer.py:235), training_loss is not
+                        li = rec["loss"][i].tolist()
+                        its = rec["iters"][i].tolist()
+                        cap = rec["trace_loss"].shape[1]
+                        R = len(li)
+                        xs = []
+                        for r in range(R):  # restarts in the reference's sequential order, up to the first success
+                            if li[r] >= 1e300:
+                                continue
+                            n = min(int(its[r]), cap)
+                            tl.extend(rec["trace_loss"][i * R + r, :n].tolist())
+                            if n:
+                                xs.append(rec["trace_x"][i * R + r, :n])
+                            if li[r] < self.success_threshold:
+                                break
+                        if xs:
+                            U = engine.template_eval(rec["desc"], torch.cat(xs).contiguous())
                             coords = [tuple(c) for c in c1c2c3_batch(U, round8=True).tolist()]
+                    self.training_loss.append(tl)
                     self.coordinate_list.append(coords)
             else:
                 self.training_loss.append(best_result)

@@ -178,3 +178,30 @@ def test_lbfgs_with_explicit_x0_is_deterministic_and_matches_scipy_minimum():
         for r in range(3):
             assert abs(O.cost(orc.eval(x[t, r]), V[t], "basic") - loss[t, r]) < 1e-12
     assert (loss.min(axis=1) < 1e-10).all()
+
+
+def test_callback_history_has_per_iteration_losses_and_coordinates():
+    """use_callback=True: training_loss[i] = [-1, k, l_1, l_2, ..., -1, k', ...] with one loss per optimiser iteration
+    (optimizer.py:217-224, 238; parsed by utils/visualize.py:90-117); coordinate_list[i] = c1c2c3 per iteration of
+    the last k tried (optimizer.py:235, 292)."""
+    np.random.seed(4)
+    opt = TemplateOptimizer(CircuitTemplate(maximum_span_guess=3, preseed=False), BasicCost(), use_callback=True,
+                            training_restarts=5)
+    tl, cl, data = opt.approximate_from_distribution(GateSample(CXGate()))
+    d = data[0]
+    assert d.success_label == 1 and d.cycles == 2
+    seq = tl[0]
+    starts = [j for j, v in enumerate(seq) if v == -1]
+    assert [seq[j + 1] for j in starts] == [1, 2]           # k = 1 tried (fails), then k = 2
+    seg1 = seq[starts[0] + 2: starts[1]]
+    seg2 = seq[starts[1] + 2:]
+    assert len(seg1) > 5 * 3 and min(seg1) > 1e-3            # all 5 restarts of k=1 recorded, none converges
+    # the trace ends at the first restart (in index order) below the threshold; restarts run concurrently on the
+    # device, so the reported best may come from a later restart that got even lower
+    assert seg2[-1] < 1e-10 and d.loss_result <= seg2[-1]
+    assert all(0.0 <= v <= 1.0 for v in seg1 + seg2)
+    # per-iteration coordinates of the last k; the final point is (locally equivalent to) CX
+    assert len(cl[0]) == len(seg2) and all(len(c) == 3 for c in cl[0])
+    assert np.allclose(cl[0][-1], (0.5, 0.0, 0.0), atol=1e-4)
+    # Armijo steps: the loss never increases along one restart
+    assert all(b <= a + 1e-15 for a, b in zip(seg2[-10:], seg2[-9:]))
