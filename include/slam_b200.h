@@ -150,6 +150,10 @@ typedef struct SlamOptOpts {
   int32_t reserved;
   double* trace_loss;
   double* trace_x;
+  /* optional box bounds, [dev] double[P] each (NULL = unbounded): projected L-BFGS, replacing the reference's
+     switch to scipy L-BFGS-B when basis.using_bounds (optimizer.py:257-258, basisv2.py:174-190); +-inf allowed.   */
+  const double* lower;
+  const double* upper;
 } SlamOptOpts;
 
 void slam_opt_defaults(SlamOptOpts* o);

@@ -54,6 +54,8 @@ class SlamOptOpts(C.Structure):
         ("reserved", C.c_int32),
         ("trace_loss", C.c_void_p),
         ("trace_x", C.c_void_p),
+        ("lower", C.c_void_p),
+        ("upper", C.c_void_p),
     ]
 
 

@@ -104,6 +104,7 @@ class CircuitTemplateV2(_CircuitTemplateBase):
         for parameter in self.circuit.parameters:
             b = self.bounds.get(parameter.name, self.default_bound) or self.default_bound
             b = (self.default_bound[0] if b[0] is None else b[0], self.default_bound[1] if b[1] is None else b[1])
+            b = (float(b[0]), float(b[1]))
             lo.append(min(b))
             hi.append(max(b))
         return np.asarray(lo, dtype=np.float64), np.asarray(hi, dtype=np.float64)

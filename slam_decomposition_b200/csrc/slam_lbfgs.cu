@@ -47,6 +47,8 @@ struct LbfgsArgs {
   int trace_cap;
   double* trace_loss;
   double* trace_x;
+  const double* lower;  // box bounds [P] or null (projected L-BFGS; the reference switches to L-BFGS-B, optimizer.py:257-258)
+  const double* upper;
   double* out_loss;
   double* out_x;
   int32_t* out_iters;
@@ -183,8 +185,13 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
         if (i < npl) {
           const int j = sub + LPP * i;
           const double gj = gt[j];
-          q[i] = gj;
-          gmax = fmax(gmax, fabs(gj));
+          double gp = gj;  // projected gradient: components pushing against an active bound are dropped
+          if (A.lower && j < P) {
+            const double xj = xt[j];
+            if ((xj <= A.lower[j] && gj > 0.0) || (xj >= A.upper[j] && gj < 0.0)) gp = 0.0;
+          }
+          q[i] = gp;
+          gmax = fmax(gmax, fabs(gp));
           if (!first) {
             const HT sf = (HT)(xt[j] - x[j]), yf = (HT)(gj - g[j]);
             s_new[j] = sf;
@@ -293,9 +300,42 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
         state = ST_LS;
         // next trial point x_new = xt + alpha d, into the old current buffer
         double* xn = base + 2 * (cur ^ 1) * Pp;
+        if (!A.lower) {
 #pragma unroll
-        for (int i = 0; i < NPL; ++i)
-          if (i < npl) xn[sub + LPP * i] = fma(alpha, q[i], xt[sub + LPP * i]);
+          for (int i = 0; i < NPL; ++i)
+            if (i < npl) xn[sub + LPP * i] = fma(alpha, q[i], xt[sub + LPP * i]);
+        } else {
+          // box constraints: project the trial point; the line search then runs along the projected segment, whose
+          // directional derivative is g.(x_new - x)/alpha
+          double gde = 0.0;
+#pragma unroll
+          for (int i = 0; i < NPL; ++i)
+            if (i < npl) {
+              const int j = sub + LPP * i;
+              double v = fma(alpha, q[i], xt[j]);
+              if (j < P) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+              xn[j] = v;
+              gde = fma(gt[j], v - xt[j], gde);
+            }
+          gde = tsum(gde, tmask) / alpha;
+          if (!(gde < 0.0)) {  // projection killed the descent: projected steepest descent
+            hcount = 0;
+            alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+            gde = 0.0;
+#pragma unroll
+            for (int i = 0; i < NPL; ++i)
+              if (i < npl) {
+                const int j = sub + LPP * i;
+                double v = fma(-alpha, gt[j], xt[j]);
+                if (j < P) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+                xn[j] = v;
+                gde = fma(gt[j], v - xt[j], gde);
+              }
+            gde = tsum(gde, tmask) / alpha;
+            if (!(gde < 0.0)) done = true;  // no feasible descent direction: a KKT point of the box problem
+          }
+          gd = gde;
+        }
       }
     } else {
       // backtrack with the cubic through (0, f, gd) and (alpha, ft, gdt), safeguarded to [0.1, 0.5] alpha;
@@ -440,6 +480,8 @@ extern "C" void slam_opt_defaults(SlamOptOpts* o) {
   o->reserved = 0;
   o->trace_loss = nullptr;
   o->trace_x = nullptr;
+  o->lower = nullptr;
+  o->upper = nullptr;
 }
 
 extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
@@ -500,6 +542,8 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
   A.trace_cap = (opts->trace_loss && opts->trace_cap > 0) ? opts->trace_cap : 0;
   A.trace_loss = opts->trace_loss; A.trace_x = opts->trace_x;
+  A.lower = (opts->lower && opts->upper) ? opts->lower : nullptr;
+  A.upper = A.lower ? opts->upper : nullptr;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved;
 

@@ -104,8 +104,8 @@ class TemplateOptimizer:
         b = self.basis
         if not isinstance(b, _CircuitTemplateBase):
             raise NotImplementedError("the device optimizer runs CircuitTemplate / CircuitTemplateV2")
-        if getattr(b, "using_bounds", False) or getattr(b, "using_constraints", False):
-            raise NotImplementedError("bounded / constrained templates (L-BFGS-B / SLSQP selection, optimizer.py:255-268)")
+        if getattr(b, "using_constraints", False):
+            raise NotImplementedError("cost-constrained templates (SLSQP selection, optimizer.py:259-264)")
         if self.override_method not in (None, "BFGS", "L-BFGS-B"):
             raise NotImplementedError(f"override_method={self.override_method}")
         ck = self._cost_kind()
@@ -146,6 +146,23 @@ class TemplateOptimizer:
             x = ws["xbuf"][: Nt * R * P].view(Nt, R, P)
             x0, lo, hi = self._x0(Nt, device)
             opts.x0_lo, opts.x0_hi = lo, hi
+            bound_t = None
+            if getattr(b, "using_bounds", False):
+                # box bounds in API order (basisv2.py:162-164); None = unbounded on that side.  The reference switches
+                # scipy to L-BFGS-B here (optimizer.py:257-258); the device optimiser projects onto the box.
+                lo_b, hi_b = [], []
+                for prm in b.circuit.parameters:
+                    bd = b.bounds.get(prm.name, None) or (None, None)
+                    l_, h_ = bd[0], bd[1]
+                    l_ = -np.inf if l_ is None else float(l_)
+                    h_ = np.inf if h_ is None else float(h_)
+                    lo_b.append(min(l_, h_))
+                    hi_b.append(max(l_, h_))
+                bound_t = (torch.as_tensor(lo_b, dtype=torch.float64, device=device),
+                           torch.as_tensor(hi_b, dtype=torch.float64, device=device))
+                opts.lower, opts.upper = bound_t[0].data_ptr(), bound_t[1].data_ptr()
+            else:
+                opts.lower, opts.upper = None, None
             seed = int(np.random.randint(0, 2 ** 62))
             trace_loss = trace_x = None
             if keep_history:

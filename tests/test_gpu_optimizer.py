@@ -116,7 +116,7 @@ def test_unsupported_objectives_and_bounds_fail_loudly():
         TemplateOptimizer(basis, object()).approximate_target_U(O.CNOT)
     b2 = CircuitTemplateV2(base_gates=[RiSwapGate])
     b2.build(2)
-    b2.add_bound("Q0", 0.5, 0.0)
+    b2.set_constraint(1.5)
     with pytest.raises(NotImplementedError):
         TemplateOptimizer(b2, BasicCost()).approximate_target_U(O.CNOT)
     with pytest.raises(ValueError):
@@ -205,3 +205,30 @@ def test_callback_history_has_per_iteration_losses_and_coordinates():
     assert np.allclose(cl[0][-1], (0.5, 0.0, 0.0), atol=1e-4)
     # Armijo steps: the loss never increases along one restart
     assert all(b <= a + 1e-15 for a, b in zip(seg2[-10:], seg2[-9:]))
+
+
+def test_bounded_v2_template_decomp_trajectory_flow():
+    """scripts/decomp_trajectory.ipynb: CircuitTemplateV2([RiSwapGate]) with every Q bounded to [0.5, 0.5] (i.e. fixed
+    sqrt(iSWAP)) reaches SWAP at k=3; and a genuine box 0 <= alpha <= 1/2 stays inside the box."""
+    np.random.seed(6)
+    basis = CircuitTemplateV2(n_qubits=2, base_gates=[RiSwapGate], edge_params=[[(0, 1)]])
+    basis.build(3)
+    basis.spanning_range = range(3, 4)
+    for el in basis.circuit.parameters:
+        if "Q" in str(el):
+            basis.add_bound(str(el), 0.5, 0.5)
+    opt = TemplateOptimizer(basis=basis, objective=SquareCost(), override_fail=True, success_threshold=1e-7, training_restarts=25)
+    d = opt.approximate_target_U(np.asarray(SwapGate()))
+    assert d.success_label == 1 and np.allclose(d.Xk[-3:], 0.5)
+    tmpl = O.OracleTemplate("riswap", ("Q",), k=3)
+    assert O.cost(tmpl.eval(d.Xk), O.SWAP, "square") <= 1e-7
+    # box: CX needs total iSWAP-angle >= 1 over k=2 => with alpha <= 1/2 both gates saturate the bound
+    b2 = CircuitTemplateV2(n_qubits=2, base_gates=[RiSwapGate])
+    b2.build(2)
+    b2.spanning_range = range(2, 3)
+    for q in ("Q0", "Q1"):
+        b2.add_bound(q, 0.5, 0.0)
+    d2 = TemplateOptimizer(b2, BasicCost(), override_fail=True, training_restarts=16).approximate_target_U(O.CNOT)
+    assert d2.success_label == 1
+    assert np.all(d2.Xk[-2:] >= -1e-15) and np.all(d2.Xk[-2:] <= 0.5 + 1e-15)
+    assert O.cost(O.OracleTemplate("riswap", ("Q",), k=2).eval(d2.Xk), O.CNOT, "basic") <= 1e-9
