@@ -56,7 +56,13 @@ typedef enum SlamGateKind {
 typedef enum SlamCostKind {
   SLAM_COST_BASIC = 0,         /* BasicCost        1 - |T|/4           cost_function.py:140-145 */
   SLAM_COST_SQUARE = 1,        /* SquareCost       1 - (|T|^2+4)/20    cost_function.py:169-173 */
-  SLAM_COST_BASIC_INVERSE = 2  /* BasicCostInverse |T|/4               cost_function.py:133-137 */
+  SLAM_COST_BASIC_INVERSE = 2, /* BasicCostInverse |T|/4               cost_function.py:133-137 */
+  /* coordinate-based functionals (forward evaluation only: slam_nm_solve), on 8-dp rounded invariants as the reference */
+  SLAM_COST_MAKHLIN_FUNCTIONAL = 3, /* MakhlinFunctionalCost  sum |g_i(V)-g_i(U)|^2   cost_function.py:219-221 */
+  SLAM_COST_MAKHLIN_EUCLIDEAN = 4,  /* MakhlinEuclideanCost   ||g(V)-g(U)||_2         cost_function.py:209-216 */
+  SLAM_COST_WEYL_EUCLIDEAN = 5,     /* WeylEuclideanCost      ||c(V)-c(U)||_2         cost_function.py:199-206 */
+  SLAM_COST_BASIC_REDUCED = 6,      /* BasicReducedCost  Basic on canonical_gate(c(.)) cost_function.py:176-182 */
+  SLAM_COST_SQUARE_REDUCED = 7      /* SquareReducedCost                               cost_function.py:185-189 */
 } SlamCostKind;
 
 /*
@@ -171,6 +177,28 @@ int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, 
                      const double* x0, int64_t ldx0, uint64_t seed, const int32_t* active,
                      const SlamOptOpts* opts, double* out_loss, double* out_x, int32_t* out_iters,
                      unsigned long long* out_evals, void* stream);
+
+/*
+ * K5b Batched Nelder-Mead with a generic forward objective: any template (incl. parameter-bound smush gates) and any
+ * SlamCostKind.  Replaces opt.minimize(method="Nelder-Mead") reached through TemplateOptimizer(override_method=...)
+ * (optimizer.py:266-278).  Simplex rules, initial simplex and the xatol/fatol termination follow scipy.
+ * Arguments as slam_lbfgs_solve.
+ */
+typedef struct SlamNmOpts {
+  int32_t max_iter;   /* reference passes options={"maxiter": 2500}                                              */
+  int32_t cost_kind;  /* any SlamCostKind                                                                        */
+  int32_t early_exit;
+  int32_t reserved;
+  double success_threshold;
+  double xatol, fatol; /* scipy defaults 1e-4, 1e-4                                                              */
+  double x0_lo, x0_hi;
+} SlamNmOpts;
+
+void slam_nm_defaults(SlamNmOpts* o);
+
+int slam_nm_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts, const double* x0,
+                  int64_t ldx0, uint64_t seed, const int32_t* active, const SlamNmOpts* opts, double* out_loss,
+                  double* out_x, int32_t* out_iters, unsigned long long* out_evals, void* stream);
 
 /*
  * K6  Fused coverage-set Monte-Carlo: Philox -> params -> template -> c1c2c3 -> fold -> bin.

@@ -12,7 +12,8 @@ SLAM_MAX_SLOTS = 24
 SLAM_MAX_PARAMS = 256
 
 GATE_RISWAP, GATE_CG, GATE_SMUSH, GATE_SMUSH_1QPHASE, GATE_FIXED = range(5)
-COST_BASIC, COST_SQUARE, COST_BASIC_INVERSE = range(3)
+(COST_BASIC, COST_SQUARE, COST_BASIC_INVERSE, COST_MAKHLIN_FUNCTIONAL, COST_MAKHLIN_EUCLIDEAN, COST_WEYL_EUCLIDEAN,
+ COST_BASIC_REDUCED, COST_SQUARE_REDUCED) = range(8)
 WEYL_FOLD, WEYL_ROUND8 = 1, 2
 
 import os
@@ -59,6 +60,20 @@ class SlamOptOpts(C.Structure):
     ]
 
 
+class SlamNmOpts(C.Structure):
+    _fields_ = [
+        ("max_iter", C.c_int32),
+        ("cost_kind", C.c_int32),
+        ("early_exit", C.c_int32),
+        ("reserved", C.c_int32),
+        ("success_threshold", C.c_double),
+        ("xatol", C.c_double),
+        ("fatol", C.c_double),
+        ("x0_lo", C.c_double),
+        ("x0_hi", C.c_double),
+    ]
+
+
 class SlamError(RuntimeError):
     pass
 
@@ -77,6 +92,9 @@ _PROTOS = {
     "slam_opt_defaults": (None, [C.POINTER(SlamOptOpts)]),
     "slam_lbfgs_solve": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_uint64, _P,
                                    C.POINTER(SlamOptOpts), _P, _P, _P, _P, _P]),
+    "slam_nm_defaults": (None, [C.POINTER(SlamNmOpts)]),
+    "slam_nm_solve": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_uint64, _P,
+                                C.POINTER(SlamNmOpts), _P, _P, _P, _P, _P]),
     "slam_coverage_mc": (C.c_int, [C.POINTER(SlamTemplateDesc), C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_double,
                                    C.c_int32, _P, _P, _P]),
     "slam_pd_trajectory": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, _P, C.c_int64, _P]),

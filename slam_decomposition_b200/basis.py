@@ -84,8 +84,31 @@ class HamiltonianTemplate(VariationalTemplate):
     def get_spanning_range(self, target_u):
         return range(1, 2)
 
-    def build(self, n_repetitions):  # nothing to build (optimizer.py:240-248 only builds circuit templates)
-        return None
+    x0_bounds = (0.0, 1.0)  # np.random.random(p_len) (basis.py:48)
+
+    def build(self, n_repetitions):
+        """Nothing to extend (optimizer.py:240-248 only builds circuit templates).  For the scalar-argument
+        conversion/gain Hamiltonians the template is lowered to a one-gate descriptor whose parameters H0, H1, ... are
+        construct_U's positional arguments, so the device optimisers can run it."""
+        from .hamiltonian import ConversionGainHamiltonian, ConversionGainPhaseHamiltonian, SnailEffectiveHamiltonian
+        from .utils.gates.custom_gates import ConversionGainGate
+
+        h = self.h if isinstance(self.h, type) else type(self.h)
+        n = h.n_params()
+        ps = [Parameter(f"H{j}") for j in range(n)]
+        if issubclass(h, ConversionGainPhaseHamiltonian):
+            gate = ConversionGainGate(ps[0], ps[1], ps[2], ps[3], ps[4])  # positional quirk kept (SURVEY App. A.4)
+        elif issubclass(h, ConversionGainHamiltonian):
+            gate = ConversionGainGate(0.0, 0.0, ps[0], ps[1], 1.0)
+        elif issubclass(h, SnailEffectiveHamiltonian):
+            gate = ConversionGainGate(0.0, 0.0, ps[0], 0.0, 1.0)
+        else:
+            raise NotImplementedError(f"{h.__name__}: vector-argument Hamiltonians cannot be driven by a flat Xk "
+                                      "(construct_U(*Xk) fails in the reference as well)")
+        self.circuit = TemplateCircuit(2)
+        self.circuit.append(gate, (0, 1))
+        self.no_exterior_1q = True
+        self.desc, self.param_names, _ = lower(self.circuit, no_exterior_1q=True)
 
     def eval(self, Xk):
         return np.asarray(self.h.construct_U(*Xk))

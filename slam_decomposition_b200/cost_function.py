@@ -80,7 +80,7 @@ def _canonical_batch(c: torch.Tensor) -> torch.Tensor:
 
 
 class BasicReducedCost(BasicCost):
-    cost_kind = None
+    cost_kind = _lib.COST_BASIC_REDUCED
 
     def unitary_fidelity_batch(self, current_u, target_u):
         ct = _canonical_batch(_weyl.c1c2c3_batch(target_u, round8=True))
@@ -89,7 +89,7 @@ class BasicReducedCost(BasicCost):
 
 
 class SquareReducedCost(SquareCost):
-    cost_kind = None
+    cost_kind = _lib.COST_SQUARE_REDUCED
 
     def unitary_fidelity_batch(self, current_u, target_u):
         ct = _canonical_batch(_weyl.c1c2c3_batch(target_u, round8=True))
@@ -105,6 +105,8 @@ class _InvariantCost(UnitaryCostFunction):
 
 
 class WeylEuclideanCost(_InvariantCost):
+    cost_kind = _lib.COST_WEYL_EUCLIDEAN
+
     def unitary_fidelity_batch(self, current_u, target_u):
         ct = _weyl.c1c2c3_batch(target_u, round8=True)
         cc = _weyl.c1c2c3_batch(current_u, round8=True)
@@ -112,6 +114,8 @@ class WeylEuclideanCost(_InvariantCost):
 
 
 class MakhlinEuclideanCost(_InvariantCost):
+    cost_kind = _lib.COST_MAKHLIN_EUCLIDEAN
+
     def unitary_fidelity_batch(self, current_u, target_u):
         gt = _weyl.g1g2g3_batch(target_u, round8=True)
         gc = _weyl.g1g2g3_batch(current_u, round8=True)
@@ -119,6 +123,8 @@ class MakhlinEuclideanCost(_InvariantCost):
 
 
 class MakhlinFunctionalCost(_InvariantCost):
+    cost_kind = _lib.COST_MAKHLIN_FUNCTIONAL
+
     def unitary_fidelity_batch(self, current_u, target_u):
         gt = _weyl.g1g2g3_batch(target_u, round8=True)
         gc = _weyl.g1g2g3_batch(current_u, round8=True)

@@ -11,10 +11,10 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import SlamOptOpts, SlamTemplateDesc, check, load
+from ._lib import SlamNmOpts, SlamOptOpts, SlamTemplateDesc, check, load
 
 __all__ = [
-    "template_eval", "loss_grad", "weyl", "lbfgs_solve", "coverage_mc", "pd_trajectory", "fp64_peak", "opt_defaults",
+    "template_eval", "loss_grad", "weyl", "lbfgs_solve", "nm_solve", "nm_defaults", "coverage_mc", "pd_trajectory", "fp64_peak", "opt_defaults",
     "require_cuda",
 ]
 
@@ -160,6 +160,39 @@ def lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: Sl
         if ev is not None:
             ev[1].record()
             LBFGS_EVENTS.append((desc.k, ev[0], ev[1]))
+    _count()
+    return loss, x, iters
+
+
+def nm_defaults() -> SlamNmOpts:
+    o = SlamNmOpts()
+    load().slam_nm_defaults(C.byref(o))
+    return o
+
+
+def nm_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: SlamNmOpts, x0: Optional[torch.Tensor] = None,
+             seed: int = 0, active: Optional[torch.Tensor] = None, evals: Optional[torch.Tensor] = None,
+             out: Optional[tuple] = None):
+    """K5b: batched Nelder-Mead, generic objective.  Returns (loss [Nt,R], x [Nt,R,P], iters [Nt,R])."""
+    V = _dev(V, torch.complex128, "V")
+    Nt = V.shape[0]
+    P = desc.n_params
+    if x0 is not None:
+        x0 = _dev(x0, torch.float64, "x0")
+        if x0.shape != (Nt, restarts, P):
+            raise ValueError(f"x0 must be [{Nt},{restarts},{P}]")
+    if active is not None:
+        active = _dev(active, torch.int32, "active")
+    if out is not None:
+        loss, x, iters = out
+    else:
+        loss = torch.empty((Nt, restarts), dtype=torch.float64, device=V.device)
+        x = torch.empty((Nt, restarts, P), dtype=torch.float64, device=V.device)
+        iters = torch.empty((Nt, restarts), dtype=torch.int32, device=V.device)
+    with torch.cuda.device(V.device):
+        lib = _enter(V)
+        check(lib.slam_nm_solve(C.byref(desc), _ptr(V), Nt, int(restarts), _ptr(x0), P, C.c_uint64(seed), _ptr(active),
+                                C.byref(opts), _ptr(loss), _ptr(x), _ptr(iters), _ptr(evals), _stream()), "slam_nm_solve")
     _count()
     return loss, x, iters
 

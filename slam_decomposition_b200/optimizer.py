@@ -80,11 +80,23 @@ class TemplateOptimizer:
         if not isinstance(self.objective, UnitaryCostFunction):
             raise ValueError("Unrecognized Cost Function")  # optimizer.py:211
         ck = self.objective.cost_kind
-        if ck not in (_lib.COST_BASIC, _lib.COST_SQUARE):
+        if ck is None:
             raise NotImplementedError(
-                f"{type(self.objective).__name__}: the device L-BFGS fuses BasicCost / SquareCost; "
-                "other functionals are available through unitary_fidelity() only")
+                f"{type(self.objective).__name__} has no device optimiser yet (unitary_fidelity() is available)")
         return ck
+
+    def _use_nelder_mead(self, desc, ck: int) -> bool:
+        """Solver choice.  The reference uses scipy BFGS with finite-difference gradients unless told otherwise
+        (optimizer.py:255-268).  Here: analytic-gradient L-BFGS whenever the functional is trace based and every gate
+        has a closed-form derivative; the derivative-free Nelder-Mead kernel for coordinate-based functionals
+        (Makhlin / Weyl / reduced), parameter-bound smush gates, and when override_method asks for it."""
+        if self.override_method == "Nelder-Mead":
+            return True
+        if ck not in (_lib.COST_BASIC, _lib.COST_SQUARE):
+            return True
+        if desc.gate_kind in (_lib.GATE_SMUSH, _lib.GATE_SMUSH_1QPHASE):
+            return any(desc.slot_param[g][s] >= 0 for g in range(desc.k) for s in range(desc.n_slots))
+        return False
 
     def _x0(self, Nt: int, device) -> tuple:
         """(x0 tensor | None, lo, hi): initial points.  Uniform-box templates use the kernel's Philox stream."""
@@ -97,16 +109,18 @@ class TemplateOptimizer:
             u = torch.rand((Nt, self.training_restarts, lo.size), dtype=torch.float64, device=device, generator=gen)
             lo_t, hi_t = torch.as_tensor(lo, device=device), torch.as_tensor(hi, device=device)
             return lo_t + (hi_t - lo_t) * u, 0.0, 1.0
+        if isinstance(b, HamiltonianTemplate):
+            return None, 0.0, 1.0  # np.random.random(p_len) (basis.py:48)
         return None, 0.0, 2 * np.pi  # CircuitTemplate: np.random.random(P) * 2 pi (basis.py:111)
 
     def _run_batch(self, V: torch.Tensor, k_range: Sequence[int], opts: Optional[_lib.SlamOptOpts] = None,
                    keep_history: bool = False) -> dict:
         b = self.basis
-        if not isinstance(b, _CircuitTemplateBase):
-            raise NotImplementedError("the device optimizer runs CircuitTemplate / CircuitTemplateV2")
+        if not isinstance(b, (_CircuitTemplateBase, HamiltonianTemplate)):
+            raise NotImplementedError("the device optimizer runs CircuitTemplate / CircuitTemplateV2 / HamiltonianTemplate")
         if getattr(b, "using_constraints", False):
             raise NotImplementedError("cost-constrained templates (SLSQP selection, optimizer.py:259-264)")
-        if self.override_method not in (None, "BFGS", "L-BFGS-B"):
+        if self.override_method not in (None, "BFGS", "L-BFGS-B", "Nelder-Mead"):
             raise NotImplementedError(f"override_method={self.override_method}")
         ck = self._cost_kind()
         device = V.device
@@ -114,7 +128,7 @@ class TemplateOptimizer:
         R = int(self.training_restarts)
         if opts is None:
             opts = engine.opt_defaults()
-        opts.cost_kind = ck
+        opts.cost_kind = ck if ck in (_lib.COST_BASIC, _lib.COST_SQUARE) else _lib.COST_BASIC
         opts.success_threshold = float(self.success_threshold)
         opts.f_stop = min(opts.f_stop, 1e-3 * float(self.success_threshold))
         # persistent workspace: output tables are reused across k and across calls (no allocator churn per sweep)
@@ -174,8 +188,17 @@ class TemplateOptimizer:
             else:
                 opts.trace_cap, opts.trace_loss, opts.trace_x = 0, None, None
             ev_before = int(evals.item()) if timing else 0
-            loss, x, iters = engine.lbfgs_solve(desc, V, R, opts, x0=x0, seed=seed, active=active, evals=evals,
-                                                out=(ws["loss"], x, ws["iters"]))
+            if self._use_nelder_mead(desc, ck):
+                if getattr(b, "using_bounds", False):
+                    raise NotImplementedError("box bounds with the Nelder-Mead kernel")
+                nm = engine.nm_defaults()
+                nm.cost_kind, nm.max_iter, nm.early_exit = ck, opts.max_iter, opts.early_exit
+                nm.success_threshold, nm.x0_lo, nm.x0_hi = float(self.success_threshold), lo, hi
+                loss, x, iters = engine.nm_solve(desc, V, R, nm, x0=x0, seed=seed, active=active, evals=evals,
+                                                 out=(ws["loss"], x, ws["iters"]))
+            else:
+                loss, x, iters = engine.lbfgs_solve(desc, V, R, opts, x0=x0, seed=seed, active=active, evals=evals,
+                                                    out=(ws["loss"], x, ws["iters"]))
             if timing:
                 self.launch_evals.append((k, int(evals.item()) - ev_before))
             lmin, rmin = loss.min(dim=1)
@@ -284,6 +307,6 @@ class TemplateOptimizer:
                 "Failed to converge within error threshold. Try increasing restart attempts or increasing temperature "
                 f"scaling on preseed. (targets {failures[:8]}{'...' if len(failures) > 8 else ''})")
         # leave the template at the size of the last target's best result, as the reference does on failure
-        if out and out[-1].cycles > 0:
+        if out and out[-1].cycles > 0 and isinstance(b, _CircuitTemplateBase):
             b.build(n_repetitions=out[-1].cycles)
         return out
