@@ -390,6 +390,21 @@ def micro_benchmarks(engine, peak_flops):
     torch.cuda.synchronize()
     t = a.elapsed_time(b) * 1e-3 / 5
     out["weyl_c1c2c3"] = {"matrices_per_s": U.shape[0] / t, "hbm_gbs": U.shape[0] * (256 + 24) / t / 1e9}
+    # K6 coverage Monte-Carlo (BASELINE configs[1]): 1e7 samples, sqrt(iSWAP) k=3, plain and smush (parallel-drive) templates
+    from slam_decomposition_b200.utils.gates import parallel_drive_volume as pdv
+
+    n = 10_000_000
+    for label, basis in (("coverage_sqiSwap_k3_plain", pdv.plain_template(math.pi / 2, 0.0, 0.5, 3)),
+                         ("coverage_sqiSwap_k3_smush", pdv.smush_template(math.pi / 2, 0.0, 0.5, 3))):
+        hist = torch.zeros(128 ** 3, dtype=torch.int64, device=dev)
+        for _ in range(3):
+            pdv.coverage_histogram(basis, 1_000_000, seed=1, hist=hist)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pdv.coverage_histogram(basis, n, seed=2023, hist=hist)
+        b.record()
+        torch.cuda.synchronize()
+        out[label] = {"samples_per_s": n / (a.elapsed_time(b) * 1e-3), "samples": n, "params": basis.desc.n_params}
     return out
 
 
