@@ -32,7 +32,7 @@ extern "C" {
 
 #define SLAM_ABI_VERSION 1
 #define SLAM_MAX_K 8      /* max 2Q-gate applications per template (reference uses <= 6)       */
-#define SLAM_MAX_SLOTS 24 /* max scalar slots of one 2Q gate (smush1q: 8 + 2T + 1, T <= 7)     */
+#define SLAM_MAX_SLOTS 40 /* max scalar slots of one 2Q gate (smush1q: 8 + 2T + 1, T <= 15)    */
 #define SLAM_MAX_PARAMS 256
 
 typedef enum SlamStatus {

@@ -8,7 +8,7 @@ import ctypes as C
 from pathlib import Path
 
 SLAM_MAX_K = 8
-SLAM_MAX_SLOTS = 24
+SLAM_MAX_SLOTS = 40
 SLAM_MAX_PARAMS = 256
 
 GATE_RISWAP, GATE_CG, GATE_SMUSH, GATE_SMUSH_1QPHASE, GATE_FIXED = range(5)

@@ -91,7 +91,7 @@ int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_
     return SLAM_OK;
   }
   // RiSwap / ConversionGain: closed form
-  bool sym = !any_bound;
+  bool sym = !any_bound && !kt->vz_only;  // the GM_SYM kernels have the RZ-layer code compiled out
   for (int g = 0; g < d->k; ++g) {
     double* c = kt->gblk[g];
     if (d->gate_kind == SLAM_GATE_RISWAP) {

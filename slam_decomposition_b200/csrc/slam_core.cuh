@@ -33,6 +33,9 @@ enum GateMode : int {
   GM_SMUSH = 3   // parameter-bound smush gate: per-slice exp(-i dt H) (forward evaluation only)
 };
 
+// Field order matters: kernel parameters beyond the first 4 KB of the parameter space are served by a slower path
+// (measured: +33 % sweep time when the hot tables crossed it), so the fields the GM_SYM hot path reads come first and
+// the big, rarely used tables (slot bindings, dense gates) last.  Kernels also take this struct as their LAST parameter.
 struct KTemplate {
   int k;         // 2Q gate applications
   int P;         // parameters
@@ -42,12 +45,12 @@ struct KTemplate {
   int n_slots;
   int vz_only;
   int n_trig;    // entries of the per-problem trig cache: 6(k+1) [+ 4k for parameter-bound block gates]
-  int gate_bound[SLAM_MAX_K];        // GM_BLOCK: 1 if any slot of gate g is a parameter
   short p1q[SLAM_MAX_K + 1][6];
-  short slot_param[SLAM_MAX_K][SLAM_MAX_SLOTS];
-  double slot_const[SLAM_MAX_K][SLAM_MAX_SLOTS];
+  int gate_bound[SLAM_MAX_K];        // GM_BLOCK: 1 if any slot of gate g is a parameter
   double gsym[SLAM_MAX_K][4];        // GM_SYM: co, so, ci, si
   double gblk[SLAM_MAX_K][8];        // GM_BLOCK constant gates: (cos,sin) of phi_c, phi_g, a_c, a_g
+  short slot_param[SLAM_MAX_K][SLAM_MAX_SLOTS];
+  double slot_const[SLAM_MAX_K][SLAM_MAX_SLOTS];
   double dense[SLAM_MAX_K][32];      // GM_DENSE
 };
 
@@ -240,8 +243,11 @@ __device__ __forceinline__ double slot_value(const KTemplate& kt, const double* 
   return p >= 0 ? xs[p] : kt.slot_const[g][s];
 }
 
-template <int LPP>
+// GM_SYM kernels are the hot instantiations: RZ layers (vz_only) and gate trig entries are compiled out of them
+// (compile_template never selects GM_SYM for vz_only templates), which keeps the tick body of K5 smaller.
+template <int LPP, int GM>
 __device__ __forceinline__ void fill_trig(const KTemplate& kt, const double* xs, double2* tg, int sub) {
+  const bool vz = (GM != GM_SYM) && kt.vz_only;
   const int n1 = 6 * (kt.k + 1);
   for (int e = sub; e < kt.n_trig; e += LPP) {
     double2 cs = make_double2(1.0, 0.0);
@@ -249,11 +255,11 @@ __device__ __forceinline__ void fill_trig(const KTemplate& kt, const double* xs,
       const int layer = e / 6, s = e - 6 * layer;
       const int p = kt.p1q[layer][s];
       if (p >= 0) {
-        const bool half = kt.vz_only ? true : (s == 0 || s == 3);
+        const bool half = vz ? true : (s == 0 || s == 3);
         const double a = half ? 0.5 * xs[p] : xs[p];
         sincos(a, &cs.y, &cs.x);
       }
-    } else {
+    } else if (GM == GM_BLOCK) {
       const int q = e - n1;
       const int g = q >> 2, w = q & 3;
       if (kt.gate_kind == SLAM_GATE_RISWAP) {
@@ -291,11 +297,12 @@ __device__ __forceinline__ void gate_apply(const KTemplate& kt, const BlockGate&
   else dense_apply<OP>(v, kt.dense[g]);
 }
 
+template <int GM>
 __device__ __forceinline__ bool build_layer(const KTemplate& kt, const double2* tg, int i, cd A[4], cd B[4]) {
   // returns false if the layer is absent (no_exterior_1q); A acts on qubit 1 (high bit), B on qubit 0
   if (kt.p1q[i][0] < 0 && kt.p1q[i][3] < 0) return false;
   const double2* t = tg + 6 * i;
-  if (kt.vz_only) {
+  if ((GM != GM_SYM) && kt.vz_only) {
     build_rz(t[0], B);
     build_rz(t[3], A);
   } else {
@@ -317,7 +324,7 @@ __device__ __forceinline__ void forward_chain(const KTemplate& kt, const double2
     for (int a = 0; a < 4; ++a) r[c][a] = mkc((a == sub * CPL + c) ? 1.0 : 0.0, 0.0);
   for (int i = 0; i <= kt.k; ++i) {
     cd A[4], B[4];
-    if (build_layer(kt, tg, i, A, B)) {
+    if (build_layer<GM>(kt, tg, i, A, B)) {
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
         apply1q<0, OP_N>(r[c], B);
@@ -360,7 +367,7 @@ template <int LPP, int GM, bool WANT_GRAD>
 __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const double* xs, double2* tg, double* gs,
                                                  const cd vcol[4 / LPP][4], int cost_kind, int sub, cd* T_out) {
   constexpr int CPL = 4 / LPP;
-  fill_trig<LPP>(kt, xs, tg, sub);
+  fill_trig<LPP, GM>(kt, xs, tg, sub);
   if (WANT_GRAD)
     for (int j = sub; j < kt.P; j += LPP) gs[j] = 0.0;
   __syncwarp();
@@ -395,7 +402,7 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
 
   for (int i = kt.k; i >= 0; --i) {
     cd A[4], B[4];
-    if (build_layer(kt, tg, i, A, B)) {
+    if (build_layer<GM>(kt, tg, i, A, B)) {
       cd EA[4], EB[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) EA[e] = EB[e] = mkc(0.0, 0.0);
@@ -429,7 +436,7 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
       // partial derivatives of this lane, then team sum
       const double2* t = tg + 6 * i;
       double d[6];
-      if (kt.vz_only) {
+      if ((GM != GM_SYM) && kt.vz_only) {
         // RZ = diag(e^{-i l/2}, e^{+i l/2}); d/dl = (i/2) diag(-e^{-i l/2}, e^{+i l/2})
         // Re(-(i/2) m00 E00 + (i/2) m11 E11) = 0.5 * (Im(m00 E00) - Im(m11 E11))
         const cd b0 = cmul(B[0], EB[0]), b3 = cmul(B[3], EB[3]);
@@ -459,7 +466,7 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
           d[3 * q + 2] = -(m01e.im + m11e.im);
         }
       }
-      if (kt.vz_only) {
+      if ((GM != GM_SYM) && kt.vz_only) {
         d[0] = team_sum<LPP>(d[0]);
         d[3] = team_sum<LPP>(d[3]);
         if (sub == 0) {

@@ -19,9 +19,9 @@ struct PhiloxParams {
   __device__ __forceinline__ double get(int j) const { return philox_param(seed, sample, j, lo, span); }
 };
 
-__global__ void __launch_bounds__(128) coverage_kernel(const __grid_constant__ KTemplate kt, uint64_t seed, int64_t first,
-                                                       int64_t n, double lo, double span, int nbins,
-                                                       unsigned long long* __restrict__ hist, double* __restrict__ coords) {
+__global__ void __launch_bounds__(128) coverage_kernel(uint64_t seed, int64_t first, int64_t n, double lo, double span,
+                                                       int nbins, unsigned long long* __restrict__ hist,
+                                                       double* __restrict__ coords, const __grid_constant__ KTemplate kt) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const double scale = 2.0 * (double)nbins;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -71,7 +71,7 @@ extern "C" int slam_coverage_mc(const SlamTemplateDesc* desc, uint64_t seed, int
   SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t want = (n_samples + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 16);  // grid-stride, a multiple of the SM count
-  coverage_kernel<<<grid, 128, 0, st>>>(kt, seed, first_sample, n_samples, lo, hi - lo, nbins, hist, coords);
+  coverage_kernel<<<grid, 128, 0, st>>>(seed, first_sample, n_samples, lo, hi - lo, nbins, hist, coords, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }

@@ -13,10 +13,9 @@ constexpr int kThreads = 128;
 
 template <int LPP, int GM, bool WANT_GRAD>
 __global__ void __launch_bounds__(kThreads)
-loss_grad_kernel(const __grid_constant__ KTemplate kt, const double* __restrict__ x, int64_t ldx,
-                 const double* __restrict__ V, int64_t Nt, const int32_t* __restrict__ tgt_idx, int cost_kind,
-                 double* __restrict__ loss, double* __restrict__ grad, int64_t ldg, double* __restrict__ trace,
-                 int64_t B) {
+loss_grad_kernel(const double* __restrict__ x, int64_t ldx, const double* __restrict__ V, int64_t Nt,
+                 const int32_t* __restrict__ tgt_idx, int cost_kind, double* __restrict__ loss, double* __restrict__ grad,
+                 int64_t ldg, double* __restrict__ trace, int64_t B, const __grid_constant__ KTemplate kt) {
   constexpr int CPL = 4 / LPP;
   const int nthr = blockDim.x;
   const int TPB = nthr / LPP;
@@ -70,8 +69,8 @@ loss_grad_kernel(const __grid_constant__ KTemplate kt, const double* __restrict_
 
 template <int LPP, int GM>
 __global__ void __launch_bounds__(kThreads)
-eval_kernel(const __grid_constant__ KTemplate kt, const double* __restrict__ x, int64_t ldx, double* __restrict__ U,
-            int64_t B) {
+eval_kernel(const double* __restrict__ x, int64_t ldx, double* __restrict__ U, int64_t B,
+            const __grid_constant__ KTemplate kt) {
   constexpr int CPL = 4 / LPP;
   const int nthr = blockDim.x;
   const int TPB = nthr / LPP;
@@ -90,7 +89,7 @@ eval_kernel(const __grid_constant__ KTemplate kt, const double* __restrict__ x, 
   __syncthreads();
   const int team = tid / LPP, sub = tid % LPP;
   double2* tgp = tg + team * kt.n_trig;
-  fill_trig<LPP>(kt, xs + team * XS, tgp, sub);
+  fill_trig<LPP, GM>(kt, xs + team * XS, tgp, sub);
   __syncwarp();
   cd r[CPL][4];
   forward_chain<LPP, GM>(kt, tgp, sub, r);
@@ -139,12 +138,12 @@ static int launch_loss_grad(const KTemplate& kt, const double* x, int64_t ldx, c
     const size_t sm = smem_bytes(kt, LPP, true, threads);
     auto kern = loss_grad_kernel<LPP, GM, true>;
     if (sm > 48 * 1024) SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kern<<<grid, threads, sm, st>>>(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B);
+    kern<<<grid, threads, sm, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, kt);
   } else {
     const size_t sm = smem_bytes(kt, LPP, false, threads);
     auto kern = loss_grad_kernel<LPP, GM, false>;
     if (sm > 48 * 1024) SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kern<<<grid, threads, sm, st>>>(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, nullptr, 0, trace, B);
+    kern<<<grid, threads, sm, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, nullptr, 0, trace, B, kt);
   }
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
@@ -170,7 +169,7 @@ static int launch_eval(const KTemplate& kt, const double* x, int64_t ldx, double
   const size_t sm = smem_bytes(kt, LPP, false, threads);
   auto kern = eval_kernel<LPP, GM>;
   if (sm > 48 * 1024) SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  kern<<<grid, threads, sm, st>>>(kt, x, ldx, U, B);
+  kern<<<grid, threads, sm, st>>>(x, ldx, U, B, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }

@@ -24,6 +24,9 @@ namespace slam {
 constexpr int LPP = 4;
 constexpr int kMaxHist = 8;
 constexpr double kArmijo = 1e-4;
+#ifndef SLAM_LBFGS_LOCKSTEP
+#define SLAM_LBFGS_LOCKSTEP 0
+#endif
 #ifndef SLAM_LBFGS_MAX_THREADS
 #define SLAM_LBFGS_MAX_THREADS 384  // register cap 168/thread -> up to 12 warps per SM
 #endif
@@ -76,9 +79,11 @@ enum { ST_IDLE = 0, ST_INIT = 1, ST_LS = 2 };
 // S, Y (2 m Pp elements of HT per team) is a second region behind the slices of all teams.  Vectors are padded to Pp = 4 ceil(P/4) entries that stay zero, so every lane owns
 // exactly npl = Pp/4 entries (j = sub + 4 i) and the vector loops need no per-lane bounds checks.
 // The search direction is not stored: while a line search is in progress it is (xt - x) / alpha.
-template <int GM, int NPL, typename HT>
-__global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid_constant__ KTemplate kt,
-                                                                    const __grid_constant__ LbfgsArgs A) {
+// EXTRAS = box bounds and/or per-iteration trace requested: compiled out of the common kernel so that the hot tick body
+// stays compact (the tick is instruction-cache bound: adding these paths inline cost 30 % even when unused).
+template <int GM, int NPL, typename HT, bool EXTRAS>
+__global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid_constant__ LbfgsArgs A,
+                                                                    const __grid_constant__ KTemplate kt) {
   extern __shared__ __align__(16) double smem[];
   const int P = kt.P, m = A.m;
   const int Pp = (P + 3) & ~3;
@@ -112,72 +117,82 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
 #pragma unroll
   for (int a = 0; a < 4; ++a) vcol[0][a] = mkc(0.0, 0.0);
 
+  // The whole tick is WARP-CONVERGENT: every lane executes every section and per-team decisions only predicate
+  // stores / scalar updates.  Team reductions can therefore use full-mask xor-1/xor-2 shuffles (which never leave a
+  // 4-lane team); team-masked shuffles inside divergent branches compile to a WARPSYNC.COLLECTIVE + BSSY/BSYNC
+  // sequence of ~10 instructions each and made up a fifth of the kernel before this restructuring.
+  constexpr unsigned FULL = 0xffffffffu;
   while (true) {
-    // ---------------- fetch work for idle teams --------------------------------------------------
-    while (state == ST_IDLE && !exhausted) {
+    // ---------------- fetch work for idle teams (convergent loop) --------------------------------
+    while (true) {
+      const bool need = (state == ST_IDLE && !exhausted);
+      if (!__any_sync(FULL, need)) break;
       unsigned long long w = 0;
-      if (sub == 0) w = atomicAdd(A.next, 1ULL);
-      w = __shfl_sync(tmask, w, lane & ~3);
-      if ((int64_t)w >= total) {
-        exhausted = true;
-        break;
-      }
-      // restart-major order: all targets' restart 0 first, then restart 1, ...  With many more targets than teams
-      // in flight this reproduces the reference's sequential restart loop with its break on first success
-      // (optimizer.py:253-295): restart r of a target is skipped once an earlier restart has solved it.
-      const int64_t r_idx = (int64_t)w / A.Nt;
-      const int64_t t = (int64_t)w - r_idx * A.Nt;
-      pid = t * A.restarts + r_idx;  // index of the (target, restart) pair in the output tables and the x0 stream
-      tgt = t;
-      bool skip = A.active && A.active[t] == 0;
-      if (!skip && A.early_exit) skip = *((volatile int32_t*)(A.solved + t)) != 0;
-      if (skip) {
-        if (sub == 0) {
-          A.out_loss[pid] = DBL_MAX;
-          A.out_iters[pid] = 0;
-        }
-        for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = 0.0;
-        continue;
-      }
-      // initial point into the trial buffer (buffer 1), target columns into registers
-      cur = 0;
-      double* xt = base + 2 * Pp;
-      for (int j = sub; j < P; j += LPP)
-        xt[j] = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
+      if (need && sub == 0) w = atomicAdd(A.next, 1ULL);
+      w = __shfl_sync(FULL, w, lane & ~3);
+      if (need) {
+        if ((int64_t)w >= total) {
+          exhausted = true;
+        } else {
+          // restart-major order: all targets' restart 0 first, then restart 1, ...  With many more targets than
+          // teams in flight this reproduces the reference's sequential restart loop with its break on first success
+          // (optimizer.py:253-295): restart r of a target is skipped once an earlier restart has solved it.
+          const int64_t r_idx = (int64_t)w / A.Nt;
+          const int64_t t = (int64_t)w - r_idx * A.Nt;
+          pid = t * A.restarts + r_idx;  // index of the (target, restart) pair in the output tables / the x0 stream
+          tgt = t;
+          bool skip = A.active && A.active[t] == 0;
+          if (!skip && A.early_exit) skip = *((volatile int32_t*)(A.solved + t)) != 0;
+          if (skip) {
+            if (sub == 0) {
+              A.out_loss[pid] = DBL_MAX;
+              A.out_iters[pid] = 0;
+            }
+            for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = 0.0;
+          } else {
+            // initial point into the trial buffer (buffer 1), target columns into registers
+            cur = 0;
+            double* x1 = base + 2 * Pp;
+            for (int j = sub; j < P; j += LPP)
+              x1[j] = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const double2 v = *reinterpret_cast<const double2*>(A.V + t * 32 + (a * 4 + sub) * 2);
-        vcol[0][a] = mkc(v.x, v.y);
+            for (int a = 0; a < 4; ++a) {
+              const double2 v = *reinterpret_cast<const double2*>(A.V + t * 32 + (a * 4 + sub) * 2);
+              vcol[0][a] = mkc(v.x, v.y);
+            }
+            state = ST_INIT;
+            iter = 0;
+            ls = 0;
+            hcount = 0;
+            hpos = 0;
+            gamma = 1.0;
+            slow = false;
+          }
+        }
       }
-      state = ST_INIT;
-      iter = 0;
-      ls = 0;
-      hcount = 0;
-      hpos = 0;
-      gamma = 1.0;
-      slow = false;
     }
-    if (__all_sync(0xffffffffu, state == ST_IDLE)) break;
-    __syncwarp();
+    if (__all_sync(FULL, state == ST_IDLE)) break;
 
-    // ---------------- one loss+grad evaluation per team (convergent) -----------------------------
+    // ---------------- one loss+grad evaluation per team -------------------------------------------
     double* xt = base + 2 * (cur ^ 1) * Pp;
     double* gt = xt + Pp;
     const double ft = loss_grad_team<LPP, GM, true>(kt, xt, tg, gt, vcol, A.cost_kind, sub, nullptr);
-    if (state == ST_IDLE) continue;
-    ++evals;
+    const bool live = (state != ST_IDLE);
+    if (live) ++evals;
 
-    // ---------------- per-team bookkeeping (divergent across teams) ------------------------------
     const double* x = base + 2 * cur * Pp;
     const double* g = x + Pp;
-    const bool first = (state == ST_INIT);
-    const bool accepted = first || (ft <= f + kArmijo * alpha * gd);  // Armijo; NaN compares false
+    const bool first = live && (state == ST_INIT);
+    const bool accepted = live && (first || (ft <= f + kArmijo * alpha * gd));  // Armijo; NaN compares false
+    const bool rejected = live && !accepted;
     bool done = false;
-    if (accepted) {
-      double q[NPL];  // this lane's slice of the working vector (entries j = sub + 4 i)
-      // history pair s = xt - x, y = gt - g into slot hpos (rounded to HT; the curvature uses the rounded values); q <- gt
+
+    // ---------------- accept path (all lanes execute; effects predicated on `accepted`) -----------
+    double q[NPL];  // this lane's slice of the working vector (entries j = sub + 4 i)
+    {
       HT* s_new = S + hpos * Pp;
       HT* y_new = Y + hpos * Pp;
+      const bool pair = accepted && !first;
       double sy = 0.0, yy = 0.0, gmax = 0.0;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
@@ -186,105 +201,121 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
           const int j = sub + LPP * i;
           const double gj = gt[j];
           double gp = gj;  // projected gradient: components pushing against an active bound are dropped
-          if (A.lower && j < P) {
+          if (EXTRAS && A.lower && j < P) {
             const double xj = xt[j];
             if ((xj <= A.lower[j] && gj > 0.0) || (xj >= A.upper[j] && gj < 0.0)) gp = 0.0;
           }
           q[i] = gp;
           gmax = fmax(gmax, fabs(gp));
-          if (!first) {
-            const HT sf = (HT)(xt[j] - x[j]), yf = (HT)(gj - g[j]);
+          const HT sf = (HT)(xt[j] - x[j]), yf = (HT)(gj - g[j]);
+          if (pair) {  // history pair s = xt - x, y = gt - g (rounded to HT; the curvature uses the rounded values)
             s_new[j] = sf;
             y_new[j] = yf;
-            sy = fma((double)sf, (double)yf, sy);
-            yy = fma((double)yf, (double)yf, yy);
           }
+          sy = fma((double)sf, (double)yf, sy);
+          yy = fma((double)yf, (double)yf, yy);
         }
       }
-      gmax = tmax(gmax, tmask);
-      if (!first) {
-        sy = tsum(sy, tmask);
-        yy = tsum(yy, tmask);
-        if (sy > 1e-14 * yy && yy > 0.0) {  // cautious update: keep only positive-curvature pairs
-          if (sub == 0) rho[hpos] = 1.0 / sy;
-          gamma = sy / yy;
-          hpos = (hpos + 1 == m) ? 0 : hpos + 1;
-          hcount = min(hcount + 1, m);
-        } else if (hcount == m) {
-          hcount = m - 1;  // the rejected pair overwrote the oldest slot
-        }
-        ++iter;
-        if (iter <= A.trace_cap) {  // per-iteration trace (the reference's callbackF)
-          const int64_t e = pid * A.trace_cap + (iter - 1);
-          if (sub == 0) A.trace_loss[e] = ft;
-          if (A.trace_x)
-            for (int j = sub; j < P; j += LPP) A.trace_x[e * P + j] = xt[j];
-        }
-      }
-      cur ^= 1;  // trial point becomes the current point
-      f = ft;
-      // progress checkpoint every 32 accepted steps: "slow" = less than 4x reduction since the last one
-      if ((iter & 31) == 0) {
-        slow = iter > 0 && f > 0.25 * f_chk;
-        f_chk = f;
-      }
-      // gtol_far is scipy's BFGS default gtol (1e-5), where the reference stops unconditionally.  Here it only
-      // ends restarts that sit at a non-zero local minimum (f > f_far) or have stopped making real progress;
-      // restarts still converging towards zero loss run on to f_stop / gtol.
-      done = (f < A.f_stop) || (gmax < A.gtol) || (gmax < A.gtol_far && (f > A.f_far || slow)) ||
-             (iter >= A.max_iter) || !(f == f);
-      if (!done && A.early_exit && (iter & 3) == 0) done = *((volatile int32_t*)(A.solved + tgt)) != 0;
-      if (!done) {
-        __syncwarp(tmask);  // s_new / y_new / rho visible to the team
-        // two-loop recursion on the register slice: q <- H g
-        for (int h = 0; h < hcount; ++h) {
-          int slot = hpos - 1 - h;
-          if (slot < 0) slot += m;
-          const HT* s = S + slot * Pp + sub;
-          const HT* y = Y + slot * Pp + sub;
-          double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-          for (int i = 0; i < NPL; i += 2) {
-            if (i < npl) a0 = fma((double)s[LPP * i], q[i], a0);
-            if (i + 1 < NPL && i + 1 < npl) a1 = fma((double)s[LPP * (i + 1)], q[i + 1], a1);
+      gmax = team_max<LPP>(gmax);
+      sy = team_sum<LPP>(sy);
+      yy = team_sum<LPP>(yy);
+      if (accepted) {
+        if (pair) {
+          if (sy > 1e-14 * yy && yy > 0.0) {  // cautious update: keep only positive-curvature pairs
+            if (sub == 0) rho[hpos] = 1.0 / sy;
+            gamma = sy / yy;
+            hpos = (hpos + 1 == m) ? 0 : hpos + 1;
+            hcount = min(hcount + 1, m);
+          } else if (hcount == m) {
+            hcount = m - 1;  // the rejected pair overwrote the oldest slot
           }
-          const double a = tsum(a0 + a1, tmask) * rho[slot];
-          if (sub == 0) alp[slot] = a;
-#pragma unroll
-          for (int i = 0; i < NPL; ++i)
-            if (i < npl) q[i] = fma(-a, (double)y[LPP * i], q[i]);
-        }
-        __syncwarp(tmask);
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) q[i] *= gamma;
-        for (int h = hcount - 1; h >= 0; --h) {
-          int slot = hpos - 1 - h;
-          if (slot < 0) slot += m;
-          const HT* s = S + slot * Pp + sub;
-          const HT* y = Y + slot * Pp + sub;
-          double b0 = 0.0, b1 = 0.0;
-#pragma unroll
-          for (int i = 0; i < NPL; i += 2) {
-            if (i < npl) b0 = fma((double)y[LPP * i], q[i], b0);
-            if (i + 1 < NPL && i + 1 < npl) b1 = fma((double)y[LPP * (i + 1)], q[i + 1], b1);
+          ++iter;
+          if (EXTRAS && iter <= A.trace_cap) {  // per-iteration trace (the reference's callbackF)
+            const int64_t e = pid * A.trace_cap + (iter - 1);
+            if (sub == 0) A.trace_loss[e] = ft;
+            if (A.trace_x)
+              for (int j = sub; j < P; j += LPP) A.trace_x[e * P + j] = xt[j];
           }
-          const double c = alp[slot] - tsum(b0 + b1, tmask) * rho[slot];
-#pragma unroll
-          for (int i = 0; i < NPL; ++i)
-            if (i < npl) q[i] = fma(c, (double)s[LPP * i], q[i]);
         }
-        // d = -q ; gd = g.d ; gg = g.g  (g = gt: the accepted gradient)
-        double gdn = 0.0, gg = 0.0;
+        cur ^= 1;  // trial point becomes the current point
+        f = ft;
+        // progress checkpoint every 32 accepted steps: "slow" = less than 4x reduction since the last one
+        if ((iter & 31) == 0) {
+          slow = iter > 0 && f > 0.25 * f_chk;
+          f_chk = f;
+        }
+        // gtol_far is scipy's BFGS default gtol (1e-5), where the reference stops unconditionally.  Here it only
+        // ends restarts that sit at a non-zero local minimum (f > f_far) or have stopped making real progress;
+        // restarts still converging towards zero loss run on to f_stop / gtol.
+        done = (f < A.f_stop) || (gmax < A.gtol) || (gmax < A.gtol_far && (f > A.f_far || slow)) ||
+               (iter >= A.max_iter) || !(f == f);
+        if (!done && A.early_exit && (iter & 3) == 0) done = *((volatile int32_t*)(A.solved + tgt)) != 0;
+      }
+    }
+    const bool step = accepted && !done;  // teams that need a new search direction
+    __syncwarp();                         // s_new / y_new / rho visible to the team
+    {
+      // two-loop recursion on the register slice: q <- H g.  Loop bound = the largest history in the warp; teams
+      // with a shorter history (or not stepping) run with a zero coefficient.
+      const int hmax = __reduce_max_sync(FULL, step ? hcount : 0);
+      for (int h = 0; h < hmax; ++h) {
+        const bool on = step && h < hcount;
+        int slot = hpos - 1 - h;
+        if (slot < 0) slot += m;
+        if (!on) slot = 0;
+        const HT* s = S + slot * Pp + sub;
+        const HT* y = Y + slot * Pp + sub;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; i += 2) {
+          if (i < npl) a0 = fma((double)s[LPP * i], q[i], a0);
+          if (i + 1 < NPL && i + 1 < npl) a1 = fma((double)s[LPP * (i + 1)], q[i + 1], a1);
+        }
+        const double asum = team_sum<LPP>(a0 + a1);
+        const double a = on ? asum * rho[slot] : 0.0;
+        if (on && sub == 0) alp[slot] = a;
 #pragma unroll
         for (int i = 0; i < NPL; ++i)
-          if (i < npl) {
-            const double gj = gt[sub + LPP * i];
-            q[i] = -q[i];
-            gdn = fma(gj, q[i], gdn);
-            gg = fma(gj, gj, gg);
-          }
-        gdn = tsum(gdn, tmask);
-        gg = tsum(gg, tmask);
+          if (i < npl) q[i] = fma(-a, (double)y[LPP * i], q[i]);
+      }
+      __syncwarp();
+      if (step) {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) q[i] *= gamma;
+      }
+      for (int h = hmax - 1; h >= 0; --h) {
+        const bool on = step && h < hcount;
+        int slot = hpos - 1 - h;
+        if (slot < 0) slot += m;
+        if (!on) slot = 0;
+        const HT* s = S + slot * Pp + sub;
+        const HT* y = Y + slot * Pp + sub;
+        double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; i += 2) {
+          if (i < npl) b0 = fma((double)y[LPP * i], q[i], b0);
+          if (i + 1 < NPL && i + 1 < npl) b1 = fma((double)y[LPP * (i + 1)], q[i + 1], b1);
+        }
+        const double bsum = team_sum<LPP>(b0 + b1);
+        const double c = on ? alp[slot] - bsum * rho[slot] : 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+          if (i < npl) q[i] = fma(c, (double)s[LPP * i], q[i]);
+      }
+      // d = -q ; gd = g.d ; gg = g.g  (g = gt: the accepted gradient)
+      double gdn = 0.0, gg = 0.0;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i)
+        if (i < npl) {
+          const double gj = gt[sub + LPP * i];
+          q[i] = -q[i];
+          gdn = fma(gj, q[i], gdn);
+          gg = fma(gj, gj, gg);
+        }
+      gdn = team_sum<LPP>(gdn);
+      gg = team_sum<LPP>(gg);
+      double* xn = base + 2 * (cur ^ 1) * Pp;  // for stepping teams: the old current buffer
+      if (step) {
         if (hcount == 0 || !(gdn < 0.0)) {  // first step or not a descent direction: steepest descent, unit length
           hcount = 0;
 #pragma unroll
@@ -298,50 +329,57 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
         gd = gdn;
         ls = 0;
         state = ST_LS;
-        // next trial point x_new = xt + alpha d, into the old current buffer
-        double* xn = base + 2 * (cur ^ 1) * Pp;
-        if (!A.lower) {
+        if (!EXTRAS || !A.lower) {  // next trial point x_new = xt + alpha d
 #pragma unroll
           for (int i = 0; i < NPL; ++i)
             if (i < npl) xn[sub + LPP * i] = fma(alpha, q[i], xt[sub + LPP * i]);
-        } else {
-          // box constraints: project the trial point; the line search then runs along the projected segment, whose
-          // directional derivative is g.(x_new - x)/alpha
-          double gde = 0.0;
-#pragma unroll
-          for (int i = 0; i < NPL; ++i)
-            if (i < npl) {
-              const int j = sub + LPP * i;
-              double v = fma(alpha, q[i], xt[j]);
-              if (j < P) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
-              xn[j] = v;
-              gde = fma(gt[j], v - xt[j], gde);
-            }
-          gde = tsum(gde, tmask) / alpha;
-          if (!(gde < 0.0)) {  // projection killed the descent: projected steepest descent
-            hcount = 0;
-            alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
-            gde = 0.0;
-#pragma unroll
-            for (int i = 0; i < NPL; ++i)
-              if (i < npl) {
-                const int j = sub + LPP * i;
-                double v = fma(-alpha, gt[j], xt[j]);
-                if (j < P) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
-                xn[j] = v;
-                gde = fma(gt[j], v - xt[j], gde);
-              }
-            gde = tsum(gde, tmask) / alpha;
-            if (!(gde < 0.0)) done = true;  // no feasible descent direction: a KKT point of the box problem
-          }
-          gd = gde;
         }
       }
-    } else {
-      // backtrack with the cubic through (0, f, gd) and (alpha, ft, gdt), safeguarded to [0.1, 0.5] alpha;
-      // the direction is recovered from the failed trial point: d = (xt - x) / alpha
+      if (EXTRAS && A.lower) {
+        // box constraints: project the trial point; the line search then runs along the projected segment, whose
+        // directional derivative is g.(x_new - x)/alpha
+        double gde = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+          if (i < npl) {
+            const int j = sub + LPP * i;
+            double v = fma(alpha, q[i], xt[j]);
+            if (j < P) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+            if (step) xn[j] = v;
+            gde = fma(gt[j], v - xt[j], gde);
+          }
+        gde = team_sum<LPP>(gde) / alpha;
+        const bool sd = step && !(gde < 0.0);  // projection killed the descent: projected steepest descent
+        const double asd = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+        double gds = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+          if (i < npl) {
+            const int j = sub + LPP * i;
+            double v = fma(-asd, gt[j], xt[j]);
+            if (j < P) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+            if (sd) xn[j] = v;
+            gds = fma(gt[j], v - xt[j], gds);
+          }
+        gds = team_sum<LPP>(gds) / asd;
+        if (step) {
+          gd = gde;
+          if (sd) {
+            hcount = 0;
+            alpha = asd;
+            gd = gds;
+            if (!(gds < 0.0)) done = true;  // no feasible descent direction: a KKT point of the box problem
+          }
+        }
+      }
+    }
+
+    // ---------------- backtrack path (all lanes execute; effects predicated on `rejected`) ---------
+    {
+      // cubic through (0, f, gd) and (alpha, ft, gdt), safeguarded to [0.1, 0.5] alpha; the direction is recovered
+      // from the failed trial point: d = (xt - x) / alpha
       double dx[NPL];
-      double gdt = 0.0;
+      double gdt = 0.0, gg = 0.0;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
         dx[i] = 0.0;
@@ -349,53 +387,49 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
           const int j = sub + LPP * i;
           dx[i] = xt[j] - x[j];
           gdt = fma(gt[j], dx[i], gdt);
+          gg = fma(g[j], g[j], gg);
         }
       }
-      gdt = tsum(gdt, tmask) / alpha;
-      double an = 0.5 * alpha;
-      if (ft == ft && gdt == gdt) {
-        const double d1 = gd + gdt - 3.0 * (ft - f) / alpha;
-        const double disc = d1 * d1 - gd * gdt;
-        if (disc >= 0.0) {
-          const double d2 = sqrt(disc);
-          const double den = gdt - gd + 2.0 * d2;
-          if (den != 0.0) {
-            const double cand = alpha - alpha * (gdt + d2 - d1) / den;
-            if (cand == cand) an = cand;
+      gdt = team_sum<LPP>(gdt);
+      gg = team_sum<LPP>(gg);
+      if (rejected) {
+        gdt /= alpha;
+        double an = 0.5 * alpha;
+        if (ft == ft && gdt == gdt) {
+          const double d1 = gd + gdt - 3.0 * (ft - f) / alpha;
+          const double disc = d1 * d1 - gd * gdt;
+          if (disc >= 0.0) {
+            const double d2 = sqrt(disc);
+            const double den = gdt - gd + 2.0 * d2;
+            if (den != 0.0) {
+              const double cand = alpha - alpha * (gdt + d2 - d1) / den;
+              if (cand == cand) an = cand;
+            }
           }
         }
-      }
-      an = fmin(fmax(an, 0.1 * alpha), 0.5 * alpha);
-      double ratio = an / alpha;
-      alpha = an;
-      ++ls;
-      bool reset = false;
-      if (ls > 30) {
-        if (hcount > 0) {  // curvature model is bad: restart from steepest descent
-          hcount = 0;
-          double gg = 0.0;
+        an = fmin(fmax(an, 0.1 * alpha), 0.5 * alpha);
+        double ratio = an / alpha;
+        alpha = an;
+        ++ls;
+        if (ls > 30) {
+          if (hcount > 0) {  // curvature model is bad: restart from steepest descent
+            hcount = 0;
+#pragma unroll
+            for (int i = 0; i < NPL; ++i)
+              if (i < npl) dx[i] = -g[sub + LPP * i];
+            gd = -gg;
+            alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+            ratio = alpha;
+            ls = 0;
+          } else {
+            done = true;  // no progress possible at working precision
+          }
+        }
+        if (!done) {
 #pragma unroll
           for (int i = 0; i < NPL; ++i)
-            if (i < npl) {
-              const double gj = g[sub + LPP * i];
-              dx[i] = -gj;
-              gg = fma(gj, gj, gg);
-            }
-          gg = tsum(gg, tmask);
-          gd = -gg;
-          alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
-          ratio = alpha;
-          ls = 0;
-          reset = true;
-        } else {
-          done = true;  // no progress possible at working precision
+            if (i < npl) xt[sub + LPP * i] = fma(ratio, dx[i], x[sub + LPP * i]);
         }
-      }
-      (void)reset;
-      if (!done) {
-#pragma unroll
-        for (int i = 0; i < NPL; ++i)
-          if (i < npl) xt[sub + LPP * i] = fma(ratio, dx[i], x[sub + LPP * i]);
       }
     }
     if (done) {
@@ -408,6 +442,7 @@ __global__ void __launch_bounds__(kLbfgsMaxThreads, 1) lbfgs_kernel(const __grid
       for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = xf[j];
       state = ST_IDLE;
     }
+    __syncwarp();
   }
   if (A.out_evals && sub == 0 && evals) atomicAdd(A.out_evals, evals);
 }
@@ -431,13 +466,19 @@ static size_t team_bytes(const KTemplate& kt, int m, int hist_bytes) {
   return (size_t)team_doubles(kt, m) * 8 + (size_t)team_hist_elems(kt, m, hist_bytes) * hist_bytes;
 }
 
-template <int GM, int NPL, typename HT>
-static int launch_lbfgs(const KTemplate& kt, const LbfgsArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
-  auto kern = lbfgs_kernel<GM, NPL, HT>;
+template <int GM, int NPL, typename HT, bool EXTRAS>
+static int launch_lbfgs_x(const KTemplate& kt, const LbfgsArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
+  auto kern = lbfgs_kernel<GM, NPL, HT, EXTRAS>;
   SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, threads, smem, st>>>(kt, A);
+  kern<<<grid, threads, smem, st>>>(A, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
+}
+
+template <int GM, int NPL, typename HT>
+static int launch_lbfgs(const KTemplate& kt, const LbfgsArgs& A, int grid, int threads, size_t smem, cudaStream_t st) {
+  if (A.lower || A.trace_cap > 0) return launch_lbfgs_x<GM, NPL, HT, true>(kt, A, grid, threads, smem, st);
+  return launch_lbfgs_x<GM, NPL, HT, false>(kt, A, grid, threads, smem, st);
 }
 
 template <int GM, typename HT>

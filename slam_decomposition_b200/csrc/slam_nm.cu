@@ -96,7 +96,7 @@ __device__ __forceinline__ double generic_cost(const cd R[4][4] /*[col][row]*/, 
   return loss;
 }
 
-__global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ KTemplate kt, const __grid_constant__ NmArgs A) {
+__global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs A, const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
   const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t T = A.T;
@@ -310,7 +310,7 @@ extern "C" int slam_nm_solve(const SlamTemplateDesc* desc, const double* V, int6
   A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved; A.ws = ws; A.T = T;
-  nm_kernel<<<(unsigned)blocks, threads, 0, st>>>(kt, A);
+  nm_kernel<<<(unsigned)blocks, threads, 0, st>>>(A, kt);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(next, st);
   cudaFreeAsync(solved, st);

@@ -7,8 +7,8 @@
 namespace slam {
 
 // ---- K1 for parameter-bound smush templates: one thread per parameter row ---------------------------
-__global__ void __launch_bounds__(128) smush_eval_kernel(const __grid_constant__ KTemplate kt, const double* __restrict__ x,
-                                                         int64_t ldx, double* __restrict__ U, int64_t B) {
+__global__ void __launch_bounds__(128) smush_eval_kernel(const double* __restrict__ x, int64_t ldx, double* __restrict__ U,
+                                                         int64_t B, const __grid_constant__ KTemplate kt) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   GlobalParams ps{x + b * ldx};
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) smush_eval_kernel(const __grid_constant__
 
 int smush_eval_launch(const KTemplate& kt, const double* x, int64_t ldx, double* U, int64_t B, cudaStream_t st) {
   const unsigned grid = (unsigned)((B + 127) / 128);
-  smush_eval_kernel<<<grid, 128, 0, st>>>(kt, x, ldx, U, B);
+  smush_eval_kernel<<<grid, 128, 0, st>>>(x, ldx, U, B, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }
@@ -33,7 +33,7 @@ struct ConstParams {
   __device__ __forceinline__ double get(int) const { return 0.0; }
 };
 
-__global__ void const_smush_kernel(const __grid_constant__ KTemplate kt, double* __restrict__ out) {
+__global__ void const_smush_kernel(double* __restrict__ out, const __grid_constant__ KTemplate kt) {
   const int g = threadIdx.x;
   if (g >= kt.k) return;
   cd R[4][4];
@@ -61,7 +61,7 @@ int lower_const_smush(const SlamTemplateDesc* d, KTemplate* kt, cudaStream_t st)
   if (int rc = keep_async_pool(device)) return rc;
   double* dev = nullptr;
   SLAM_CUDA_CHECK(cudaMallocAsync((void**)&dev, sizeof(double) * 32 * SLAM_MAX_K, st));
-  const_smush_kernel<<<1, SLAM_MAX_K, 0, st>>>(tmp, dev);
+  const_smush_kernel<<<1, SLAM_MAX_K, 0, st>>>(dev, tmp);
   SLAM_CUDA_CHECK(cudaGetLastError());
   SLAM_CUDA_CHECK(cudaMemcpyAsync(kt->dense, dev, sizeof(double) * 32 * kt->k, cudaMemcpyDeviceToHost, st));
   SLAM_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -135,3 +135,39 @@ def test_parallel_driven_gate_widget_matches_reference_semantics():
     assert np.allclose(O.c1c2c3(w0.solve_end()), (0.5, 0.5, 0.0), atol=1e-8)
     c, U = trajectories(np.zeros((3, 8)), np.ones((3, 4)), np.ones((3, 4)))
     assert c.shape == (3, 4, 5, 3) and U.shape == (3, 4, 4)
+
+
+def test_drive_amplitude_search_with_makhlin_cost():
+    """scripts/parallel_drive_swap (cells 7-10): search the per-slice drive amplitudes of a parallel-driven iSWAP pulse
+    (N = 10 slices of 0.1) for a target class with a Makhlin cost and Nelder-Mead.  The N-slice widget circuit is one
+    ConversionGainSmush1QPhaseGate with T = N, so TemplateOptimizer drives it through the generic Nelder-Mead kernel."""
+    from slam_decomposition_b200.basisv2 import CircuitTemplateV2
+    from slam_decomposition_b200.cost_function import MakhlinEuclideanCost
+    from slam_decomposition_b200.optimizer import TemplateOptimizer
+    from slam_decomposition_b200.utils.pd_playground import ParallelDrivenGateWidget
+
+    N, dt = 10, 0.1
+
+    def pulse(*v):
+        return ConversionGainSmush1QPhaseGate(0, 0, 0, 0, np.pi / 2, 0, 0, 0, v[:N], v[N:], t_el=N * dt)
+
+    basis = CircuitTemplateV2(n_qubits=2, base_gates=[pulse], no_exterior_1q=True, param_vec_expand=[0, N, N])
+    basis.build(1)
+    basis.spanning_range = range(1, 2)
+    assert basis.desc.n_params == 2 * N and basis.desc.T == N
+    # the template with amplitudes x equals the widget's solve_end() with the same non-uniform drive
+    x = np.linspace(-3, 3, 2 * N)
+    names = [p.name for p in basis.circuit.parameters]
+    natural = np.array([x[int(n[1:])] for n in names])  # Xk is name-sorted (Q0, Q1, Q10, ...)
+    w = ParallelDrivenGateWidget(N=N, gc=np.pi / 2)
+    w.prepare_parameters_nonuniform(x[:N], x[N:])
+    assert np.abs(basis.eval(natural) - w.solve_end()).max() < 1e-10
+    # search: reach the CNOT class (the "ImprovedCX" use case, pd_playground.py:251-258) from random amplitudes
+    np.random.seed(12)
+    for b in names:
+        basis.bounds[b] = (-4.0, 4.0)  # initial-point box only (no add_bound -> unbounded optimisation)
+    opt = TemplateOptimizer(basis, MakhlinEuclideanCost(), override_fail=True, training_restarts=64, success_threshold=1e-7)
+    d = opt.approximate_target_U(O.CNOT)
+    U = basis.eval(d.Xk)
+    assert abs(O.cost(U, O.CNOT, "makhlin_euclidean") - d.loss_result) < 3e-8
+    assert d.loss_result < 5e-3 and np.allclose(O.fold_c1(np.array(O.c1c2c3(U))), (0.5, 0.0, 0.0), atol=5e-3)

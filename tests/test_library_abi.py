@@ -39,8 +39,8 @@ def test_abi_version_and_status_strings(lib):
 
 
 def test_struct_layouts_match_the_header():
-    # SlamTemplateDesc: 8 int32 + int32[9][6] + int32[8][24] + double[8][24] + double[32]
-    assert ctypes.sizeof(_lib.SlamTemplateDesc) == 32 + 9 * 6 * 4 + 8 * 24 * 4 + 8 * 24 * 8 + 32 * 8
+    # SlamTemplateDesc: 8 int32 + int32[9][6] + int32[8][40] + double[8][40] + double[32]
+    assert ctypes.sizeof(_lib.SlamTemplateDesc) == 32 + 9 * 6 * 4 + 8 * 40 * 4 + 8 * 40 * 8 + 32 * 8
     assert _lib.SlamTemplateDesc.slot_const.offset % 8 == 0
     assert ctypes.sizeof(_lib.SlamOptOpts) == 4 * 4 + 7 * 8 + 2 * 4 + 4 * 8
 
