@@ -34,8 +34,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 SQCNOT = (0.0, 0.0, math.pi / 4, math.pi / 4, 0.5)
-# dram bytes (read + write) of one lbfgs_kernel launch (k = 1, 1e5 targets x 16 restarts) from the committed ncu capture
-NCU_DRAM_BYTES_K1_LAUNCH = 69_999_872 + 136_897_792
+# dram bytes (read + write) of one lbfgs_kernel launch (k = 3, 1e5 targets x 16 restarts) from the committed ncu capture
+NCU_DRAM_BYTES_K3_LAUNCH = 59_524_864 + 284_939_520
 K_MAX = 6
 RESTARTS = 16
 
@@ -318,10 +318,11 @@ def run_ours(args):
             "bound": "fp64", "kernel": "slam::lbfgs_kernel (K5: loss+grad adjoint + L-BFGS, state in shared memory)",
             "achieved": alg_flops / (kern_ms * 1e-3) / 1e12 if kern_ms else None, "peak": peak_flops / 1e12,
             "unit": "TFLOP/s", "frac": (alg_flops / (kern_ms * 1e-3)) / peak_flops if kern_ms else None,
-            "traffic": NCU_DRAM_BYTES_K1_LAUNCH, "traffic_unit": "bytes/launch",
-            "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of the k=1 lbfgs_kernel launch of this workload "
+            "traffic": NCU_DRAM_BYTES_K3_LAUNCH, "traffic_unit": "bytes/launch",
+            "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of the k=3 lbfgs_kernel launch of this workload "
                              "(1e5 targets x 16 restarts) from one ncu --set full capture, profiles/r01_lbfgs_kernel_ncu_full.txt; "
-                             "algorithmic bytes of that launch = result table 1.6e6 x (12+1) x 8 B + iters = 173 MB + targets 25.6 MB"),
+                             "algorithmic bytes of that launch = result table 1.6e6 x (24+1) x 8 B + iters 6.4 MB = 326 MB "
+                             "+ targets 25.6 MB: the kernel is compute bound, DRAM throughput 0.1 % of peak"),
             "peak_source": "slam_fp64_peak: register-resident DFMA loop measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
             "flop_model": "SURVEY 8(d): F_lossgrad(k) = 1024k + 124(k+1) + 128 + 512(5k+3) + 768(k+1) per evaluation",
             "kernel_share_of_step": kern_ms * 1e-3 / t_local if t_local else None,

@@ -118,13 +118,15 @@ static int pick_threads(const KTemplate& kt, int lpp, bool grad) {
   return t;
 }
 
-static int pick_lpp() {
+// lanes per problem for the streaming kernels: measured on B200 (scripts/quick_bench.py, loss+grad, % of DFMA peak)
+//   k=1: LPP 4/2/1 = 55/62/57 %   k=3: 71/79/65 %   k=6: 79/70/46 %   -> 2 lanes up to k=4, 4 lanes beyond
+static int pick_lpp(const KTemplate& kt) {
   const char* e = getenv("SLAM_B200_LPP");
   if (e) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) return v;
   }
-  return 4;
+  return kt.k <= 4 ? 2 : 4;
 }
 
 template <int LPP, int GM>
@@ -218,7 +220,7 @@ extern "C" int slam_loss_grad(const SlamTemplateDesc* desc, const double* x, int
     rc = lower_const_smush(desc, &kt, st);
     if (rc != SLAM_OK) return rc;
   }
-  switch (pick_lpp()) {
+  switch (pick_lpp(kt)) {
     case 1: return dispatch_loss_grad<1>(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, st);
     case 2: return dispatch_loss_grad<2>(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, st);
     default: return dispatch_loss_grad<4>(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, st);

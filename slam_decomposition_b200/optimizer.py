@@ -148,6 +148,7 @@ class TemplateOptimizer:
         per_k = []
         ar = ws["ar"]
         timing = engine.LBFGS_EVENTS is not None
+        marks = []
         for k in k_range:
             logging.info(f"Starting opt on template size {k}")
             b.build(n_repetitions=k)
@@ -187,7 +188,6 @@ class TemplateOptimizer:
                 opts.trace_cap, opts.trace_loss, opts.trace_x = cap, trace_loss.data_ptr(), trace_x.data_ptr()
             else:
                 opts.trace_cap, opts.trace_loss, opts.trace_x = 0, None, None
-            ev_before = int(evals.item()) if timing else 0
             if self._use_nelder_mead(desc, ck):
                 if getattr(b, "using_bounds", False):
                     raise NotImplementedError("box bounds with the Nelder-Mead kernel")
@@ -200,7 +200,7 @@ class TemplateOptimizer:
                 loss, x, iters = engine.lbfgs_solve(desc, V, R, opts, x0=x0, seed=seed, active=active, evals=evals,
                                                     out=(ws["loss"], x, ws["iters"]))
             if timing:
-                self.launch_evals.append((k, int(evals.item()) - ev_before))
+                marks.append((k, evals.clone()))  # async snapshot; converted to per-launch deltas after the sweep
             lmin, rmin = loss.min(dim=1)
             improved = (active != 0) & (lmin < best_loss)
             xsel = x[ar, rmin]
@@ -225,6 +225,11 @@ class TemplateOptimizer:
                 logging.info(f"Break on cycle {k}")
                 break
         self.last_stats = {"evals": int(evals.item())}
+        prev = 0
+        for k_, snap in marks:
+            cur_ = int(snap.item())
+            self.launch_evals.append((k_, cur_ - prev))
+            prev = cur_
         return {"best_loss": best_loss.cpu().numpy(), "best_k": best_k.cpu().numpy(), "best_P": best_P.cpu().numpy(),
                 "best_x": best_x, "per_k": per_k, "best_loss_dev": best_loss, "best_k_dev": best_k}
 
