@@ -18,17 +18,17 @@ from slam_decomposition_b200.optimizer import TemplateOptimizer
 from slam_decomposition_b200.utils.gates.custom_gates import ConversionGainGate
 
 CONFIGS = {
-    "lpp4_generic": {"SLAM_B200_LBFGS_LPP": "4", "SLAM_B200_LBFGS_EXACT": "0"},
-    "lpp4_exact": {"SLAM_B200_LBFGS_LPP": "4", "SLAM_B200_LBFGS_EXACT": "1"},
-    "lpp4_exact_hi32": {"SLAM_B200_LBFGS_LPP": "4", "SLAM_B200_LBFGS_EXACT": "1", "SLAM_B200_LBFGS_HIST": "1"},
-    "lpp2_exact_m4": {"SLAM_B200_LBFGS_LPP": "2", "SLAM_B200_LBFGS_EXACT": "1", "SLAM_B200_LBFGS_MMIN": "4"},
-    "lpp2_exact_m3": {"SLAM_B200_LBFGS_LPP": "2", "SLAM_B200_LBFGS_EXACT": "1", "SLAM_B200_LBFGS_MMIN": "3"},
-    "lpp2_exact_m3_hi32": {"SLAM_B200_LBFGS_LPP": "2", "SLAM_B200_LBFGS_EXACT": "1", "SLAM_B200_LBFGS_MMIN": "3",
-                           "SLAM_B200_LBFGS_HIST": "1"},
-    "lpp2_generic_m3": {"SLAM_B200_LBFGS_LPP": "2", "SLAM_B200_LBFGS_EXACT": "0", "SLAM_B200_LBFGS_MMIN": "3"},
-    "lpp4_exact_m3": {"SLAM_B200_LBFGS_LPP": "4", "SLAM_B200_LBFGS_EXACT": "1", "SLAM_B200_LBFGS_MMIN": "3"},
+    "x384": {},
+    "x384_f32": {"SLAM_B200_LBFGS_HIST": "0"},
+    "generic": {"SLAM_B200_LBFGS_EXACT": "0"},
+    "x512_m6": {"SLAM_B200_LBFGS_MAXT": "512", "SLAM_B200_LBFGS_MMIN": "6"},
+    "x512_m5": {"SLAM_B200_LBFGS_MAXT": "512", "SLAM_B200_LBFGS_MMIN": "5"},
+    "x512_m4": {"SLAM_B200_LBFGS_MAXT": "512", "SLAM_B200_LBFGS_MMIN": "4"},
+    "x512_m3": {"SLAM_B200_LBFGS_MAXT": "512", "SLAM_B200_LBFGS_MMIN": "3"},
+    "lpp2_m3": {"SLAM_B200_LBFGS_LPP": "2", "SLAM_B200_LBFGS_MMIN": "3"},
 }
-KEYS = ("SLAM_B200_LBFGS_LPP", "SLAM_B200_LBFGS_EXACT", "SLAM_B200_LBFGS_HIST", "SLAM_B200_LBFGS_MMIN", "SLAM_B200_LBFGS_TEAMS")
+KEYS = ("SLAM_B200_LBFGS_LPP", "SLAM_B200_LBFGS_EXACT", "SLAM_B200_LBFGS_HIST", "SLAM_B200_LBFGS_MMIN", "SLAM_B200_LBFGS_TEAMS",
+        "SLAM_B200_LBFGS_MAXT")
 
 
 def main():

@@ -116,6 +116,78 @@ __device__ __forceinline__ void build_rz(double2 h, cd m[4]) {  // h = (cos, sin
   m[3] = mkc(h.x, h.y);
 }
 
+// Factored U3: U(theta, phi, lam) = D(phi) Ry(theta) D(lam) with D(a) = diag(1, e^{ia}), Ry = [[c,-s],[s,c]], (c,s) =
+// (cos,sin)(theta/2).  Applying the three factors costs the same 16 FP64 instructions per amplitude pair as a general
+// complex 2x2 but needs no matrix build, and in the backward sweep the cuts between the factors give every parameter
+// derivative as a short diagonal / antisymmetric contraction of the row vector w and the column vector r at the SAME cut:
+//   T = w_x . r_x at every cut x;   dT/dphi = i sum_hi w r (cut after D(phi));   dT/dlam = i sum_hi w r and
+//   dT/dtheta = 1/2 sum_pairs (w_hi r_lo - w_lo r_hi) (cut between D(lam) and Ry, since dRy/dtheta = Ry J / 2).
+// "hi" = the two amplitudes whose bit Q is set; pairs (lo, hi) differ in bit Q.
+template <int Q, bool CONJ>
+__device__ __forceinline__ void phase1q(cd v[4], double2 e) {  // hi <- e^{+-ia} hi
+  const double s = CONJ ? -e.y : e.y;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int hi = (Q == 0) ? 2 * p + 1 : p + 2;
+    const cd b = v[hi];
+    v[hi] = mkc(fma(e.x, b.re, -(s * b.im)), fma(e.x, b.im, s * b.re));
+  }
+}
+template <int Q, bool TR>
+__device__ __forceinline__ void rot1q(cd v[4], double2 t) {  // (lo,hi) <- Ry (lo,hi), or Ry^T when TR
+  const double s = TR ? -t.y : t.y;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int lo = (Q == 0) ? 2 * p : p;
+    const int hi = (Q == 0) ? 2 * p + 1 : p + 2;
+    const cd a = v[lo], b = v[hi];
+    v[lo] = mkc(fma(t.x, a.re, -(s * b.re)), fma(t.x, a.im, -(s * b.im)));
+    v[hi] = mkc(fma(t.x, b.re, s * a.re), fma(t.x, b.im, s * a.im));
+  }
+}
+// column vector: v <- U3 v (qubit Q); t[0..2] = (cos,sin) of theta/2, phi, lam
+template <int Q>
+__device__ __forceinline__ void u3_fwd(cd v[4], const double2* t) {
+  phase1q<Q, false>(v, t[2]);
+  rot1q<Q, false>(v, t[0]);
+  phase1q<Q, false>(v, t[1]);
+}
+// sum over the hi amplitudes of Im(w r), and the antisymmetric pair sum Re(w_hi r_lo - w_lo r_hi)
+template <int Q>
+__device__ __forceinline__ double diag_im(const cd w[4], const cd r[4], double acc) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int hi = (Q == 0) ? 2 * p + 1 : p + 2;
+    acc = fma(w[hi].re, r[hi].im, fma(w[hi].im, r[hi].re, acc));
+  }
+  return acc;
+}
+template <int Q>
+__device__ __forceinline__ double anti_re(const cd w[4], const cd r[4], double acc) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int lo = (Q == 0) ? 2 * p : p;
+    const int hi = (Q == 0) ? 2 * p + 1 : p + 2;
+    acc = fma(w[hi].re, r[lo].re, fma(-w[hi].im, r[lo].im, acc));
+    acc = fma(-w[lo].re, r[hi].re, fma(w[lo].im, r[hi].im, acc));
+  }
+  return acc;
+}
+// backward through the U3 of qubit Q: r <- U3^dagger r, w <- w U3, accumulating this lane's partial derivatives
+// (d[0] theta, d[1] phi, d[2] lam; the 1/2 of theta and the signs are applied by the caller)
+template <int Q>
+__device__ __forceinline__ void u3_bwd(cd r[4], cd w[4], const double2* t, double d[3]) {
+  d[1] = diag_im<Q>(w, r, d[1]);
+  phase1q<Q, true>(r, t[1]);
+  phase1q<Q, false>(w, t[1]);
+  rot1q<Q, true>(r, t[0]);
+  rot1q<Q, true>(w, t[0]);
+  d[2] = diag_im<Q>(w, r, d[2]);
+  d[0] = anti_re<Q>(w, r, d[0]);
+  phase1q<Q, true>(r, t[2]);
+  phase1q<Q, false>(w, t[2]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // 2Q gates
 // ------------------------------------------------------------------------------------------------
@@ -245,8 +317,21 @@ __device__ __forceinline__ double slot_value(const KTemplate& kt, const double* 
 
 // GM_SYM kernels are the hot instantiations: RZ layers (vz_only) and gate trig entries are compiled out of them
 // (compile_template never selects GM_SYM for vz_only templates), which keeps the tick body of K5 smaller.
-template <int LPP, int GM>
+// CANON = canonical parameter layout: the caller keeps x (and the gradient) in circuit creation order, entry 6*layer+slot,
+// every layer present, no parameter-bound gate -- no index tables are read (K5 permutes to/from the API order at the
+// problem boundaries).
+template <int LPP, int GM, bool CANON = false>
 __device__ __forceinline__ void fill_trig(const KTemplate& kt, const double* xs, double2* tg, int sub) {
+  if (CANON) {
+    const int n1 = 6 * (kt.k + 1);
+    for (int e = sub; e < n1; e += LPP) {
+      double2 cs;
+      const double a = (e % 3 == 0) ? 0.5 * xs[e] : xs[e];
+      sincos(a, &cs.y, &cs.x);
+      tg[e] = cs;
+    }
+    return;
+  }
   const bool vz = (GM != GM_SYM) && kt.vz_only;
   const int n1 = 6 * (kt.k + 1);
   for (int e = sub; e < kt.n_trig; e += LPP) {
@@ -292,30 +377,23 @@ __device__ __forceinline__ BlockGate load_block(const KTemplate& kt, const doubl
 
 template <int GM, int OP>
 __device__ __forceinline__ void gate_apply(const KTemplate& kt, const BlockGate& bg, int g, cd v[4]) {
+  // (CANON callers pass g = 0: one constant gate for every repetition, read as immediate constant-bank operands)
   if (GM == GM_SYM) sym_apply<OP>(v, kt.gsym[g][0], kt.gsym[g][1], kt.gsym[g][2], kt.gsym[g][3]);
   else if (GM == GM_BLOCK) block_apply<OP>(v, bg);
   else dense_apply<OP>(v, kt.dense[g]);
 }
 
 template <int GM>
-__device__ __forceinline__ bool build_layer(const KTemplate& kt, const double2* tg, int i, cd A[4], cd B[4]) {
-  // returns false if the layer is absent (no_exterior_1q); A acts on qubit 1 (high bit), B on qubit 0
-  if (kt.p1q[i][0] < 0 && kt.p1q[i][3] < 0) return false;
-  const double2* t = tg + 6 * i;
-  if ((GM != GM_SYM) && kt.vz_only) {
-    build_rz(t[0], B);
-    build_rz(t[3], A);
-  } else {
-    build_u3(t[0], t[1], t[2], B);
-    build_u3(t[3], t[4], t[5], A);
-  }
-  return true;
+__device__ __forceinline__ bool layer_present(const KTemplate& kt, int i) {  // false: dropped by no_exterior_1q
+  return !(kt.p1q[i][0] < 0 && kt.p1q[i][3] < 0);
 }
+template <int GM>
+__device__ __forceinline__ bool layer_is_rz(const KTemplate& kt) { return (GM != GM_SYM) && kt.vz_only; }
 
 // ------------------------------------------------------------------------------------------------
 // forward sweep: r[c] = column (sub*CPL + c) of U(x)
 // ------------------------------------------------------------------------------------------------
-template <int LPP, int GM>
+template <int LPP, int GM, bool CANON = false>
 __device__ __forceinline__ void forward_chain(const KTemplate& kt, const double2* tg, int sub, cd r[4 / LPP][4]) {
   constexpr int CPL = 4 / LPP;
 #pragma unroll
@@ -323,19 +401,30 @@ __device__ __forceinline__ void forward_chain(const KTemplate& kt, const double2
 #pragma unroll
     for (int a = 0; a < 4; ++a) r[c][a] = mkc((a == sub * CPL + c) ? 1.0 : 0.0, 0.0);
   for (int i = 0; i <= kt.k; ++i) {
-    cd A[4], B[4];
-    if (build_layer<GM>(kt, tg, i, A, B)) {
+    if (CANON || layer_present<GM>(kt, i)) {
+      const double2* t = tg + 6 * i;
+      if (!CANON && layer_is_rz<GM>(kt)) {
+        cd A[4], B[4];
+        build_rz(t[0], B);
+        build_rz(t[3], A);
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        apply1q<0, OP_N>(r[c], B);
-        apply1q<1, OP_N>(r[c], A);
+        for (int c = 0; c < CPL; ++c) {
+          apply1q<0, OP_N>(r[c], B);
+          apply1q<1, OP_N>(r[c], A);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          u3_fwd<0>(r[c], t);
+          u3_fwd<1>(r[c], t + 3);
+        }
       }
     }
     if (i < kt.k) {
       BlockGate bg;
       if (GM == GM_BLOCK) bg = load_block(kt, tg, i);
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_N>(kt, bg, i, r[c]);
+      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_N>(kt, bg, CANON ? 0 : i, r[c]);
     }
   }
 }
@@ -363,17 +452,17 @@ __device__ __forceinline__ void cost_from_abs(int cost_kind, double a, double& l
 //   vcol[c][a] = V[a][sub*CPL + c]  (this lane's target columns)
 // returns loss (identical on every lane of the team); *T_out = Tr(V^dag U)
 // ------------------------------------------------------------------------------------------------
-template <int LPP, int GM, bool WANT_GRAD>
+template <int LPP, int GM, bool WANT_GRAD, bool CANON = false>
 __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const double* xs, double2* tg, double* gs,
                                                  const cd vcol[4 / LPP][4], int cost_kind, int sub, cd* T_out) {
   constexpr int CPL = 4 / LPP;
-  fill_trig<LPP, GM>(kt, xs, tg, sub);
-  if (WANT_GRAD)
+  fill_trig<LPP, GM, CANON>(kt, xs, tg, sub);
+  if (WANT_GRAD && !CANON)  // (canonical layout: every entry is stored below)
     for (int j = sub; j < kt.P; j += LPP) gs[j] = 0.0;
   __syncwarp();
 
   cd r[CPL][4];
-  forward_chain<LPP, GM>(kt, tg, sub, r);
+  forward_chain<LPP, GM, CANON>(kt, tg, sub, r);
 
   // T = Tr(V^dag U) = sum_col sum_a conj(V[a][col]) U[a][col]
   cd Tp = mkc(0.0, 0.0);
@@ -401,82 +490,54 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
     for (int a = 0; a < 4; ++a) w[c][a] = cmulc(ph, vcol[c][a]);
 
   for (int i = kt.k; i >= 0; --i) {
-    cd A[4], B[4];
-    if (build_layer<GM>(kt, tg, i, A, B)) {
-      cd EA[4], EB[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) EA[e] = EB[e] = mkc(0.0, 0.0);
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        // un-peel in two steps: r holds rho = (A (x) B) r_i, so (A^dagger (x) I) rho = (I (x) B) r_i is exactly the
-        // vector v needed by the A-environment; the second step then gives r_i (columns of R_i)
-        apply1q<1, OP_H>(r[c], A);
-        cd v[4], u[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          v[a] = r[c][a];
-          u[a] = w[c][a];
-        }
-        apply1q<0, OP_H>(r[c], B);
-        apply1q<1, OP_T>(u, A);  // u = w (A (x) I)
-        // EA[a][a'] = sum_b w[(a,b)] v[(a',b)] ; EB[b][b'] = sum_a' u[(a',b)] r[(a',b')]
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int a2 = 0; a2 < 2; ++a2)
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              cacc(EA[a * 2 + a2], w[c][2 * a + b], v[2 * a2 + b]);
-              cacc(EB[a * 2 + a2], u[2 * b + a], r[c][2 * b + a2]);
-            }
-        apply1q<0, OP_T>(u, B);  // w <- w L_i
-#pragma unroll
-        for (int a = 0; a < 4; ++a) w[c][a] = u[a];
-      }
-      // partial derivatives of this lane, then team sum
+    if (CANON || layer_present<GM>(kt, i)) {
       const double2* t = tg + 6 * i;
-      double d[6];
-      if ((GM != GM_SYM) && kt.vz_only) {
-        // RZ = diag(e^{-i l/2}, e^{+i l/2}); d/dl = (i/2) diag(-e^{-i l/2}, e^{+i l/2})
-        // Re(-(i/2) m00 E00 + (i/2) m11 E11) = 0.5 * (Im(m00 E00) - Im(m11 E11))
-        const cd b0 = cmul(B[0], EB[0]), b3 = cmul(B[3], EB[3]);
-        const cd a0 = cmul(A[0], EA[0]), a3 = cmul(A[3], EA[3]);
-        d[0] = 0.5 * (b0.im - b3.im);
-        d[3] = 0.5 * (a0.im - a3.im);
-        d[1] = d[2] = d[4] = d[5] = 0.0;
+      if (!CANON && layer_is_rz<GM>(kt)) {
+        // RZ = diag(e^{-i l/2}, e^{+i l/2}); d/dl = (i/2) diag(-e^{-i l/2}, e^{+i l/2}).  With r, w at the cut after
+        // the layer: dT/dl = (i/2) (sum_hi w r - sum_lo w r)  ->  d loss = -(1/2) (Im sum_hi - Im sum_lo)
+        cd A[4], B[4];
+        build_rz(t[0], B);
+        build_rz(t[3], A);
+        double d0 = 0.0, d3 = 0.0;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          double all = 0.0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) all = fma(w[c][a].re, r[c][a].im, fma(w[c][a].im, r[c][a].re, all));
+          d0 += all - 2.0 * diag_im<0>(w[c], r[c], 0.0);  // Im sum_lo - Im sum_hi (qubit 0)
+          d3 += all - 2.0 * diag_im<1>(w[c], r[c], 0.0);
+          apply1q<1, OP_H>(r[c], A);
+          apply1q<0, OP_H>(r[c], B);
+          apply1q<1, OP_T>(w[c], A);
+          apply1q<0, OP_T>(w[c], B);
+        }
+        d0 = team_sum<LPP>(0.5 * d0);
+        d3 = team_sum<LPP>(0.5 * d3);
+        if (sub == 0) {
+          if (kt.p1q[i][0] >= 0) gs[kt.p1q[i][0]] = d0;
+          if (kt.p1q[i][3] >= 0) gs[kt.p1q[i][3]] = d3;
+        }
       } else {
+        double dq[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          u3_bwd<1>(r[c], w[c], t + 3, dq[1]);
+          u3_bwd<0>(r[c], w[c], t, dq[0]);
+        }
+        double d[6];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const cd* M = q == 0 ? B : A;
-          const cd* E = q == 0 ? EB : EA;
-          const double ch = t[3 * q].x, sh = t[3 * q].y;  // cos, sin of theta/2
-          // M01 = -e^{il} s, M10 = e^{ip} s, M11 = e^{i(p+l)} c.  With t01 = e^{il}E01 etc:
-          //  d/dtheta = 0.5*( -s Re(E00) - c Re(t01) + c Re(t10) - s Re(t11) )
-          //  d/dphi   = Re(i (M10 E10 + M11 E11)) = -Im(M10 E10 + M11 E11)
-          //  d/dlam   = Re(i (M01 E01 + M11 E11)) = -Im(M01 E01 + M11 E11)
-          const cd m01e = cmul(M[1], E[1]), m10e = cmul(M[2], E[2]), m11e = cmul(M[3], E[3]);
-          // e^{il}E01 = -M01E01/s ... avoid the division: use trig directly
-          const double2 pp = t[3 * q + 1], ll = t[3 * q + 2];
-          const cd t01 = cmul(mkc(ll.x, ll.y), E[1]);
-          const cd t10 = cmul(mkc(pp.x, pp.y), E[2]);
-          const double er = fma(pp.x, ll.x, -(pp.y * ll.y)), ei = fma(pp.y, ll.x, pp.x * ll.y);
-          const cd t11 = cmul(mkc(er, ei), E[3]);
-          d[3 * q + 0] = 0.5 * (ch * (t10.re - t01.re) - sh * (E[0].re + t11.re));
-          d[3 * q + 1] = -(m10e.im + m11e.im);
-          d[3 * q + 2] = -(m01e.im + m11e.im);
+          d[3 * q + 0] = 0.5 * dq[q][0];
+          d[3 * q + 1] = -dq[q][1];
+          d[3 * q + 2] = -dq[q][2];
         }
-      }
-      if ((GM != GM_SYM) && kt.vz_only) {
-        d[0] = team_sum<LPP>(d[0]);
-        d[3] = team_sum<LPP>(d[3]);
-        if (sub == 0) {
-          if (kt.p1q[i][0] >= 0) gs[kt.p1q[i][0]] = d[0];
-          if (kt.p1q[i][3] >= 0) gs[kt.p1q[i][3]] = d[3];
-        }
-      } else {
         reduce_scatter6<LPP>(d, sub, [&](int s, double v) {
-          const int p = kt.p1q[i][s];
-          if (p >= 0) gs[p] = v;
+          if (CANON) {
+            gs[6 * i + s] = v;
+          } else {
+            const int p = kt.p1q[i][s];
+            if (p >= 0) gs[p] = v;
+          }
         });
       }
     }
@@ -485,7 +546,7 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
       BlockGate bg;
       if (GM == GM_BLOCK) bg = load_block(kt, tg, g);
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_H>(kt, bg, g, r[c]);  // r <- G^dagger r
+      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_H>(kt, bg, CANON ? 0 : g, r[c]);  // r <- G^dagger r
       if (GM == GM_BLOCK && kt.gate_bound[g]) {
         // environment of the gate: E[i][j] = sum_c w[c][i] r[c][j] on the block pattern
         cd Ed_o = mkc(0, 0), Ed_i = mkc(0, 0), E03 = mkc(0, 0), E30 = mkc(0, 0), E12 = mkc(0, 0), E21 = mkc(0, 0);
@@ -530,7 +591,7 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
         }
       }
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_T>(kt, bg, g, w[c]);  // w <- w G
+      for (int c = 0; c < CPL; ++c) gate_apply<GM, OP_T>(kt, bg, CANON ? 0 : g, w[c]);  // w <- w G
     }
   }
   __syncwarp();

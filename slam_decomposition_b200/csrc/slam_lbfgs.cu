@@ -20,18 +20,30 @@ static int tile_stride(int n, int elem_bytes, int lpp) {
   return n;
 }
 
-// doubles per team: vectors, rho, alp, (cos, sin) cache
+// doubles per team: vectors, alp (padded to an even count: the trig cache is read as double2), (cos, sin) cache
 static int team_doubles(const KTemplate& kt, int Pp, int m, int lpp) {
-  return tile_stride(4 * Pp + 2 * m + 2 * kt.n_trig, 8, lpp);
+  return tile_stride(4 * Pp + m + (m & 1) + 2 * kt.n_trig, 8, lpp);
 }
 
-// history elements per team (second region, own stride)
+// history elements per team (second region, own stride): S, Y and rho
 static int team_hist_elems(int Pp, int m, int hist_bytes, int lpp) {
-  return tile_stride(2 * m * Pp, hist_bytes, lpp);
+  return tile_stride(2 * m * Pp + m, hist_bytes, lpp);
 }
 
 static size_t team_bytes(const KTemplate& kt, int Pp, int m, int hist_bytes, int lpp) {
   return (size_t)team_doubles(kt, Pp, m, lpp) * 8 + (size_t)team_hist_elems(Pp, m, hist_bytes, lpp) * hist_bytes;
+}
+
+// canonical template: full U3 layers around one constant symmetric gate, P = 6(k+1)
+static bool is_canonical(const KTemplate& kt) {
+  if (kt.gmode != GM_SYM || kt.vz_only || kt.P != 6 * (kt.k + 1)) return false;
+  for (int i = 0; i <= kt.k; ++i)
+    for (int s = 0; s < 6; ++s)
+      if (kt.p1q[i][s] < 0) return false;
+  for (int g = 1; g < kt.k; ++g)
+    for (int c = 0; c < 4; ++c)
+      if (kt.gsym[g][c] != kt.gsym[0][c]) return false;
+  return true;
 }
 
 bool lbfgs_has_exact(int lpp, int npl) {
@@ -95,13 +107,14 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   int lpp = env_int("SLAM_B200_LBFGS_LPP", 4);
   if (lpp != 2 && lpp != 4) return SLAM_ERR_INVALID;
   if (lpp == 2 && kt.P > 56) lpp = 4;
-  const int hist_kind = (kt.gmode == GM_SYM && !extras) ? env_int("SLAM_B200_LBFGS_HIST", 0) : 0;  // 0 float, 1 hi32
+  // history storage: upper half of the double (HistHi32); the exact GM_SYM kernels also exist with float pairs for A/B runs
+  const int hist_kind = (kt.gmode == GM_SYM && !extras) ? env_int("SLAM_B200_LBFGS_HIST", 1) : 1;  // 0 float, 1 hi32
   const int hb = 4;
   LbfgsCfg cfg;
   cfg.lpp = lpp;
   cfg.extras = extras ? 1 : 0;
   cfg.npl = (kt.P + lpp - 1) / lpp;
-  cfg.exact = (kt.gmode == GM_SYM && !extras && lbfgs_has_exact(lpp, cfg.npl) && env_int("SLAM_B200_LBFGS_EXACT", 1)) ? 1 : 0;
+  cfg.exact = (is_canonical(kt) && !extras && lbfgs_has_exact(lpp, cfg.npl) && env_int("SLAM_B200_LBFGS_EXACT", 1)) ? 1 : 0;
   int Pp = lpp * cfg.npl;
   if (!cfg.exact) {
     Pp = (kt.P + 3) & ~3;
@@ -109,12 +122,17 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   }
   // history length and teams per CTA from the shared-memory budget (one persistent CTA per SM)
   const int tpw = 32 / lpp;  // teams per warp
-  int max_teams = (lpp == 4 ? kMaxT4 : kMaxT2) / lpp;
+  cfg.maxt = lpp == 4 ? kMaxT4 : kMaxT2;
+  // 16 warps/SM (512 threads, 128 registers) where the exact kernels exist and 128 teams fit in shared memory with a
+  // history of >= 3 pairs (P <= 24); measured per k against 12 warps with m = 5..6: k=1 19.9 -> 17.5 ms, k=2 42.5 -> 38.3,
+  // k=3 38.3 -> 36.2 per 1e5-target launch (the shorter history costs 9-14 % more evaluations and still wins)
+  if (lpp == 4 && cfg.exact && cfg.npl <= 6 && env_int("SLAM_B200_LBFGS_MAXT", 512) == 512) cfg.maxt = kMaxT4x;
+  int max_teams = cfg.maxt / lpp;
   {
     const int cap = env_int("SLAM_B200_LBFGS_TEAMS", 0);
     if (cap >= tpw && cap < max_teams) max_teams = cap / tpw * tpw;
   }
-  const int m_min = std::max(1, std::min(env_int("SLAM_B200_LBFGS_MMIN", 4), 6));
+  const int m_min = std::max(1, std::min(env_int("SLAM_B200_LBFGS_MMIN", cfg.maxt == kMaxT4x ? 3 : 4), 6));
   int m = opts->history ? opts->history : 6;
   int teams = max_teams;
   if (!opts->history)  // prefer a full complement of teams (occupancy) over a longer history, down to m_min

@@ -36,7 +36,7 @@ struct LbfgsArgs {
   int64_t Nt;
   int restarts;
   int m;        // history length
-  int RS;       // doubles of shared memory per team (vectors, rho, alp, trig cache)
+  int RS;       // doubles of shared memory per team (vectors, alp, trig cache)
   int HS;       // history elements (of HT) per team; the history slices follow the RS slices of all teams
   int Pp;       // padded vector length (multiple of LPP; exactly LPP * NPL for EXACT kernels)
   int max_iter;
@@ -59,8 +59,10 @@ struct LbfgsArgs {
 // launch configuration chosen on the host (slam_lbfgs.cu)
 struct LbfgsCfg {
   int lpp;      // lanes per problem: 2 or 4
+  int maxt;     // CTA size the kernel is compiled for (4 lanes: 384 or 512)
   int npl;      // vector entries per lane held in registers
-  int exact;    // npl == Pp / lpp known at compile time (no per-entry guards)
+  int exact;    // canonical template (P = 6(k+1), every layer present, one constant symmetric gate) with npl == Pp / lpp
+                // known at compile time: no per-entry guards, no index tables, vectors kept in circuit creation order
   int extras;   // bounds and/or trace
   int grid, threads;
   size_t smem;
@@ -88,10 +90,12 @@ enum { ST_IDLE = 0, ST_INIT = 1, ST_LS = 2 };
 
 // LPP  = lanes per problem; MAXT = CTA size the kernel is compiled for (register cap = 64K / MAXT);
 // NPL  = vector entries per lane held in registers (Pp <= LPP * NPL; Pp == LPP * NPL when EXACT);
+// EXACT also selects the canonical parameter layout of slam_core.cuh (CANON): x, g and the history are kept in circuit
+// creation order and permuted to/from the API (name-sorted) order only when a problem is fetched or retired;
 // H    = storage policy of the (s, y) history.
 //
-// Shared-memory slice of a team (doubles): [x0 | g0 | x1 | g1] 4 Pp, rho[m], alp[m], (cos, sin) cache; the history
-// S, Y (2 m Pp elements per team) is a second region behind the slices of all teams.  Vectors are padded to Pp entries
+// Shared-memory slice of a team (doubles): [x0 | g0 | x1 | g1] 4 Pp, alp[m], (cos, sin) cache; the history
+// S, Y, rho (2 m Pp + m elements per team) is a second region behind the slices of all teams.  Vectors are padded to Pp entries
 // that stay zero, so every lane owns exactly npl = Pp/LPP entries (j = sub + LPP i) and the vector loops need no
 // per-lane bounds checks.  The search direction is not stored: while a line search is in progress it is (xt - x)/alpha.
 // EXTRAS = box bounds and/or per-iteration trace requested: compiled out of the common kernel so that the hot tick body
@@ -112,9 +116,9 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
   // history slices live in their own region with a stride that tiles the 32 banks for HT-sized accesses
   HT* S = reinterpret_cast<HT*>(smem + (size_t)(blockDim.x / LPP) * A.RS) + (size_t)team * A.HS;
   HT* Y = S + m * Pp;
-  double* rho = base + 4 * Pp;
-  double* alp = rho + m;
-  double2* tg = reinterpret_cast<double2*>(alp + m);
+  HT* rho = Y + m * Pp;  // 1 / (s.y) per pair, stored like the pairs themselves
+  double* alp = base + 4 * Pp;
+  double2* tg = reinterpret_cast<double2*>(alp + (m + (m & 1)));
 
   // zero the slice once: the padding entries of every vector must stay zero
   for (int j = sub; j < A.RS; j += LPP) base[j] = 0.0;
@@ -171,8 +175,10 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
             // initial point into the trial buffer (buffer 1), target columns into registers
             cur = 0;
             double* x1 = base + 2 * Pp;
-            for (int j = sub; j < P; j += LPP)
-              x1[j] = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
+            for (int c = sub; c < P; c += LPP) {
+              const int j = EXACT ? kt.p1q[c / 6][c % 6] : c;  // API index of internal entry c
+              x1[c] = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
+            }
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
 #pragma unroll
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
     // ---------------- one loss+grad evaluation per team -------------------------------------------
     double* xt = base + 2 * (cur ^ 1) * Pp;
     double* gt = xt + Pp;
-    const double ft = loss_grad_team<LPP, GM, true>(kt, xt, tg, gt, vcol, A.cost_kind, sub, nullptr);
+    const double ft = loss_grad_team<LPP, GM, true, EXACT>(kt, xt, tg, gt, vcol, A.cost_kind, sub, nullptr);
     const bool live = (state != ST_IDLE);
     if (live) ++evals;
 
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
       if (accepted) {
         if (pair) {
           if (sy > 1e-14 * yy && yy > 0.0) {  // cautious update: keep only positive-curvature pairs
-            if (sub == 0) rho[hpos] = 1.0 / sy;
+            if (sub == 0) rho[hpos] = H::pack(1.0 / sy);
             gamma = sy / yy;
             hpos = (hpos + 1 == m) ? 0 : hpos + 1;
             hcount = min(hcount + 1, m);
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
           if (i + 1 < NPL && (EXACT || i + 1 < npl)) a1 = fma(H::unpack(s[LPP * (i + 1)]), q[i + 1], a1);
         }
         const double asum = team_sum<LPP>(a0 + a1);
-        const double a = on ? asum * rho[slot] : 0.0;
+        const double a = on ? asum * H::unpack(rho[slot]) : 0.0;
         if (on && sub == 0) alp[slot] = a;
 #pragma unroll
         for (int i = 0; i < NPL; ++i)
@@ -317,7 +323,7 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
           if (i + 1 < NPL && (EXACT || i + 1 < npl)) b1 = fma(H::unpack(y[LPP * (i + 1)]), q[i + 1], b1);
         }
         const double bsum = team_sum<LPP>(b0 + b1);
-        const double c = on ? alp[slot] - bsum * rho[slot] : 0.0;
+        const double c = on ? alp[slot] - bsum * H::unpack(rho[slot]) : 0.0;
 #pragma unroll
         for (int i = 0; i < NPL; ++i)
           if (EXACT || i < npl) q[i] = fma(c, H::unpack(s[LPP * i]), q[i]);
@@ -459,7 +465,7 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
         A.out_iters[pid] = iter;
         if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + tgt, 1);
       }
-      for (int j = sub; j < P; j += LPP) A.out_x[pid * P + j] = xf[j];
+      for (int c = sub; c < P; c += LPP) A.out_x[pid * P + (EXACT ? kt.p1q[c / 6][c % 6] : c)] = xf[c];
       state = ST_IDLE;
     }
     __syncwarp();
@@ -481,6 +487,7 @@ static int launch_lbfgs(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg&
 // (register cap 255; each lane carries two matrix columns and the kernels use 200-211; ptxas applies the 384-thread cap of 168
 // registers to any CTA size above 256, which spills)
 constexpr int kMaxT4 = 384;
+constexpr int kMaxT4x = 512;  // register cap 128: only the exact GM_SYM kernels fit without spills
 constexpr int kMaxT2 = 256;
 
 // generic (guarded) instantiations; `EX` adds the exact-length ones used by the headline templates P = 6(k+1)
@@ -500,7 +507,10 @@ static int dispatch_generic(const KTemplate& kt, const LbfgsArgs& A, const Lbfgs
 template <int GM, class H>
 static int dispatch_exact(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, cudaStream_t st) {
 #define SLAM_EXACT(L, MT, N) \
-  if (c.lpp == L && c.npl == N) return launch_lbfgs<L, MT, GM, N, true, H, false>(kt, A, c, st);
+  if (c.lpp == L && c.maxt == MT && c.npl == N) return launch_lbfgs<L, MT, GM, N, true, H, false>(kt, A, c, st);
+  SLAM_EXACT(4, kMaxT4x, 3)  // 16 warps/SM where 128 teams fit in shared memory (k <= 3)
+  SLAM_EXACT(4, kMaxT4x, 5)
+  SLAM_EXACT(4, kMaxT4x, 6)
   SLAM_EXACT(4, kMaxT4, 3)   // P = 12
   SLAM_EXACT(4, kMaxT4, 5)   // P = 18 (padded to 20)
   SLAM_EXACT(4, kMaxT4, 6)   // P = 24

@@ -5,8 +5,8 @@ namespace slam {
 
 int lbfgs_launch_dense(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, int hist_kind, cudaStream_t st) {
   (void)hist_kind;
-  if (c.extras) return dispatch_generic<GM_DENSE, HistF32, true>(kt, A, c, st);
-  return dispatch_generic<GM_DENSE, HistF32, false>(kt, A, c, st);
+  if (c.extras) return dispatch_generic<GM_DENSE, HistHi32, true>(kt, A, c, st);
+  return dispatch_generic<GM_DENSE, HistHi32, false>(kt, A, c, st);
 }
 
 }  // namespace slam
