@@ -230,6 +230,13 @@ int slam_pd_trajectory(const double* gate, const double* gx, const double* gy, i
  */
 int slam_fp64_peak(int32_t iters, double* flops, double* ms);
 
+/*
+ * Diagnostic: HOST evaluation of the (cos, sin) routine the kernels use for the U3 angles (Cody-Waite reduction +
+ * fdlibm kernel polynomials, coefficients in the constant bank on the device), so that its accuracy can be checked
+ * against libm without a GPU.  x, s, c are host pointers to n doubles.  No device work.
+ */
+int slam_selftest_sincos(const double* x, int64_t n, double* s, double* c);
+
 #ifdef __cplusplus
 }
 #endif

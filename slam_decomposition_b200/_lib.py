@@ -99,6 +99,7 @@ _PROTOS = {
                                    C.c_int32, _P, _P, _P]),
     "slam_pd_trajectory": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, _P, C.c_int64, _P]),
     "slam_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "slam_selftest_sincos": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

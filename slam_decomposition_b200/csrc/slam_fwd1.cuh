@@ -162,7 +162,7 @@ __device__ __forceinline__ void fwd1_layer(const KTemplate& kt, const PS& ps, in
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
       const double v = ps.get(kt.p1q[i][q]);
-      sincos((q == 0 || q == 3) ? 0.5 * v : v, &s, &c);
+      fast_sincos((q == 0 || q == 3) ? 0.5 * v : v, &s, &c);
       t[q] = make_double2(c, s);
     }
     build_u3(t[0], t[1], t[2], B);

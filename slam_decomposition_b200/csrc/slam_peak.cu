@@ -56,3 +56,9 @@ extern "C" int slam_fp64_peak(int32_t iters, double* flops, double* ms_out) {
   if (ms_out) *ms_out = best;
   return SLAM_OK;
 }
+
+extern "C" int slam_selftest_sincos(const double* x, int64_t n, double* s, double* c) {
+  if (!x || !s || !c || n < 0) return SLAM_ERR_INVALID;
+  for (int64_t i = 0; i < n; ++i) slam::fast_sincos(x[i], s + i, c + i);
+  return SLAM_OK;
+}

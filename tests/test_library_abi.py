@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 from slam_decomposition_b200 import _lib, build
@@ -74,3 +76,39 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_fast_sincos_matches_libm():
+    """The kernels' (cos, sin) routine (slam_core.cuh fast_sincos), evaluated on the host through the diagnostic
+    entry point: within 1 ulp-ish of libm over the fast-path range, exact hand-off to libm outside it."""
+    import ctypes as C
+
+    from slam_decomposition_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    xs = np.concatenate([
+        rng.uniform(-8 * np.pi, 8 * np.pi, 2_000_000), rng.uniform(-105615.0, 105615.0, 2_000_000),
+        rng.uniform(-1e-3, 1e-3, 100_000), np.arange(-4000, 4001) * (np.pi / 4), np.arange(-4000, 4001) * (np.pi / 2),
+        np.array([0.0, -0.0, 1e-300, 105615.0, -105615.0, 105616.0, 1e9, -3e15]),
+    ])
+    s = np.empty_like(xs)
+    c = np.empty_like(xs)
+    rc = lib.slam_selftest_sincos(xs.ctypes.data_as(C.c_void_p), xs.size, s.ctypes.data_as(C.c_void_p),
+                                  c.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    rs, rc_ = np.sin(xs), np.cos(xs)
+    # absolute error bound: 1 ulp of a value in [0.5, 1) is 1.1e-16; allow 2.3e-16 (reduction + polynomial)
+    assert np.max(np.abs(s - rs)) < 2.3e-16
+    assert np.max(np.abs(c - rc_)) < 2.3e-16
+    # relative accuracy near the zeros of sin / cos (no cancellation blow-up from the reduction)
+    big = np.abs(rs) > 1e-12
+    assert np.max(np.abs(s[big] - rs[big]) / np.abs(rs[big])) < 1e-15
+    bigc = np.abs(rc_) > 1e-12
+    assert np.max(np.abs(c[bigc] - rc_[bigc]) / np.abs(rc_[bigc])) < 1e-15
+    assert np.all(s * s + c * c - 1.0 < 5e-16)
+    nan_s = np.empty(2)
+    nan_c = np.empty(2)
+    bad = np.array([np.nan, np.inf])
+    lib.slam_selftest_sincos(bad.ctypes.data_as(C.c_void_p), 2, nan_s.ctypes.data_as(C.c_void_p), nan_c.ctypes.data_as(C.c_void_p))
+    assert np.all(np.isnan(nan_s)) and np.all(np.isnan(nan_c))
