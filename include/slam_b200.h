@@ -179,6 +179,20 @@ int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, 
                      unsigned long long* out_evals, void* stream);
 
 /*
+ * K5c Batched L-BFGS with FINITE-DIFFERENCE gradients over the generic forward objective: the reference's own algorithm
+ * class (scipy BFGS with jac=None: P forward differences of step 1.49e-8 per gradient, optimizer.py:270-278) for the
+ * templates whose gates have no closed-form derivative here -- parameter-bound ConversionGainSmush /
+ * ConversionGainSmush1QPhase gates (hamiltonian.py:114-182) -- and for BasicCostInverse x circuit_fidelity
+ * (optimizer.py:200-201).  cost_kind must be trace based (BASIC, SQUARE, BASIC_INVERSE).  central != 0 selects central
+ * differences (2P evaluations per gradient, step 6e-6).  Box bounds (opts->lower/upper) by projection; the trace
+ * fields of opts are ignored.  Other arguments as slam_lbfgs_solve; out_evals counts forward evaluations.
+ */
+int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
+                        const double* x0, int64_t ldx0, uint64_t seed, const int32_t* active,
+                        const SlamOptOpts* opts, int32_t central, double* out_loss, double* out_x,
+                        int32_t* out_iters, unsigned long long* out_evals, void* stream);
+
+/*
  * K5b Batched Nelder-Mead with a generic forward objective: any template (incl. parameter-bound smush gates) and any
  * SlamCostKind.  Replaces opt.minimize(method="Nelder-Mead") reached through TemplateOptimizer(override_method=...)
  * (optimizer.py:266-278).  Simplex rules, initial simplex and the xatol/fatol termination follow scipy.

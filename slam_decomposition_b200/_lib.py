@@ -92,6 +92,8 @@ _PROTOS = {
     "slam_opt_defaults": (None, [C.POINTER(SlamOptOpts)]),
     "slam_lbfgs_solve": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_uint64, _P,
                                    C.POINTER(SlamOptOpts), _P, _P, _P, _P, _P]),
+    "slam_fd_lbfgs_solve": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_uint64, _P,
+                                      C.POINTER(SlamOptOpts), C.c_int32, _P, _P, _P, _P, _P]),
     "slam_nm_defaults": (None, [C.POINTER(SlamNmOpts)]),
     "slam_nm_solve": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_uint64, _P,
                                 C.POINTER(SlamNmOpts), _P, _P, _P, _P, _P]),

@@ -14,10 +14,9 @@
 // operation is a coalesced stream.
 #include <cfloat>
 
-#include "slam_fwd1.cuh"
 #include "slam_host.h"
+#include "slam_objective.cuh"
 #include "slam_philox.cuh"
-#include "slam_weyl.cuh"
 
 namespace slam {
 
@@ -39,62 +38,6 @@ struct NmArgs {
   double* ws;   // workspace: (n + 5) vectors of n doubles + (n + 1) function values per thread, interleaved
   int64_t T;    // threads in the grid (interleave stride)
 };
-
-struct StridedParams {
-  const double* p;
-  int64_t stride;
-  __device__ __forceinline__ double get(int j) const { return p[(int64_t)j * stride]; }
-};
-
-// cost of U against a target described by (V, its Weyl coords, its Makhlin invariants)
-struct TargetInfo {
-  const double* V;  // 32 doubles, row-major
-  double c[3], g[3];
-};
-
-__device__ __forceinline__ double generic_cost(const cd R[4][4] /*[col][row]*/, const TargetInfo& t, int kind) {
-  if (kind <= SLAM_COST_BASIC_INVERSE) {
-    cd T = mkc(0.0, 0.0);
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const cd v = mkc(t.V[(r * 4 + c) * 2], t.V[(r * 4 + c) * 2 + 1]);
-        const cd u = R[c][r];
-        T.re = fma(v.re, u.re, fma(v.im, u.im, T.re));
-        T.im = fma(v.re, u.im, fma(-v.im, u.re, T.im));
-      }
-    double loss, dl;
-    cost_from_abs(kind, sqrt(fma(T.re, T.re, T.im * T.im)), loss, dl);
-    return loss;
-  }
-  cd M[4][4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) M[r][c] = R[c][r];
-  double cc[3], gg[3];
-  const bool need_g = (kind == SLAM_COST_MAKHLIN_FUNCTIONAL || kind == SLAM_COST_MAKHLIN_EUCLIDEAN);
-  weyl_makhlin(M, SLAM_WEYL_ROUND8, need_g ? nullptr : cc, need_g ? gg : nullptr);  // 8-dp rounded, as the reference
-  if (kind == SLAM_COST_MAKHLIN_FUNCTIONAL || kind == SLAM_COST_MAKHLIN_EUCLIDEAN) {
-    const double d0 = t.g[0] - gg[0], d1 = t.g[1] - gg[1], d2 = t.g[2] - gg[2];
-    const double s = d0 * d0 + d1 * d1 + d2 * d2;
-    return kind == SLAM_COST_MAKHLIN_FUNCTIONAL ? s : sqrt(s);
-  }
-  const double d0 = cc[0] - t.c[0], d1 = cc[1] - t.c[1], d2 = cc[2] - t.c[2];
-  if (kind == SLAM_COST_WEYL_EUCLIDEAN) return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-  // canonical-reduced costs: Tr(Can(c_t)^dagger Can(c_u)) from the coordinate differences (cost_function.py:176-189)
-  const double h = 1.5707963267948966;
-  const double a0 = h * (d0 - d1 + d2), a1 = h * (d0 + d1 - d2), a2 = -h * (d0 + d1 + d2), a3 = h * (-d0 + d1 + d2);
-  double s, c, tr = 0.0, ti = 0.0;
-  sincos(a0, &s, &c); tr += c; ti += s;
-  sincos(a1, &s, &c); tr += c; ti += s;
-  sincos(a2, &s, &c); tr += c; ti += s;
-  sincos(a3, &s, &c); tr += c; ti += s;
-  double loss, dl;
-  cost_from_abs(kind == SLAM_COST_BASIC_REDUCED ? SLAM_COST_BASIC : SLAM_COST_SQUARE, sqrt(tr * tr + ti * ti), loss, dl);
-  return loss;
-}
 
 __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs A, const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
@@ -122,28 +65,11 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs 
       continue;
     }
     TargetInfo ti;
-    ti.V = A.V + t * 32;
-    if (A.cost_kind > SLAM_COST_BASIC_INVERSE) {
-      cd M[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) M[r][c] = mkc(ti.V[(r * 4 + c) * 2], ti.V[(r * 4 + c) * 2 + 1]);
-      weyl_makhlin(M, SLAM_WEYL_ROUND8, ti.c, ti.g);
-    }
+    target_info_init(ti, A.V + t * 32, A.cost_kind);
     auto f_at = [&](int v) -> double {
       StridedParams ps{&vec(v, 0), T};
-      cd R[4][4];
-      fwd1_chain(kt, ps, R);
       ++evals;
-      const double c = generic_cost(R, ti, A.cost_kind);
-      if (A.cost_kind != SLAM_COST_BASIC_INVERSE) return c;
-      // BasicCostInverse: objf = 1 - fidelity * circuit_fidelity(x) (optimizer.py:200-201), where circuit_fidelity is
-      // the product over riswap gates of RiSwapGate(alpha).cost() = alpha (basisv2.py:129-141)
-      double F = 1.0;
-      if (kt.gate_kind == SLAM_GATE_RISWAP)
-        for (int g = 0; g < kt.k; ++g) F *= slot_val(kt, ps, g, 0);
-      return 1.0 - c * F;
+      return objective_value(kt, ps, ti, A.cost_kind);
     };
     // initial simplex (scipy: y[k] *= 1.05, or 0.00025 if zero)
     for (int j = 0; j < n; ++j) {

@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import SlamNmOpts, SlamOptOpts, SlamTemplateDesc, check, load
 
 __all__ = [
-    "template_eval", "loss_grad", "weyl", "lbfgs_solve", "nm_solve", "nm_defaults", "coverage_mc", "pd_trajectory", "fp64_peak", "opt_defaults",
+    "template_eval", "loss_grad", "weyl", "lbfgs_solve", "fd_lbfgs_solve", "nm_solve", "nm_defaults", "coverage_mc", "pd_trajectory", "fp64_peak", "opt_defaults",
     "require_cuda",
 ]
 
@@ -160,6 +160,38 @@ def lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: Sl
         if ev is not None:
             ev[1].record()
             LBFGS_EVENTS.append((desc.k, ev[0], ev[1]))
+    _count()
+    return loss, x, iters
+
+
+def fd_lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: SlamOptOpts,
+                   x0: Optional[torch.Tensor] = None, seed: int = 0, active: Optional[torch.Tensor] = None,
+                   evals: Optional[torch.Tensor] = None, out: Optional[tuple] = None, central: bool = False):
+    """K5c: batched L-BFGS with finite-difference gradients over the generic forward objective (parameter-bound smush
+    gates, BasicCostInverse).  Returns (loss [Nt,R], x [Nt,R,P], iters [Nt,R]); `evals` counts forward evaluations."""
+    V = _dev(V, torch.complex128, "V")
+    Nt = V.shape[0]
+    P = desc.n_params
+    if x0 is not None:
+        x0 = _dev(x0, torch.float64, "x0")
+        if x0.shape != (Nt, restarts, P):
+            raise ValueError(f"x0 must be [{Nt},{restarts},{P}]")
+    if active is not None:
+        active = _dev(active, torch.int32, "active")
+    if out is not None:
+        loss, x, iters = out
+        if (loss.shape != (Nt, restarts) or x.shape != (Nt, restarts, P) or iters.shape != (Nt, restarts)
+                or not (loss.is_contiguous() and x.is_contiguous() and iters.is_contiguous())):
+            raise ValueError("fd_lbfgs_solve: preallocated outputs have the wrong shape")
+    else:
+        loss = torch.empty((Nt, restarts), dtype=torch.float64, device=V.device)
+        x = torch.empty((Nt, restarts, P), dtype=torch.float64, device=V.device)
+        iters = torch.empty((Nt, restarts), dtype=torch.int32, device=V.device)
+    with torch.cuda.device(V.device):
+        lib = _enter(V)
+        check(lib.slam_fd_lbfgs_solve(C.byref(desc), _ptr(V), Nt, int(restarts), _ptr(x0), P, C.c_uint64(seed), _ptr(active),
+                                      C.byref(opts), int(bool(central)), _ptr(loss), _ptr(x), _ptr(iters), _ptr(evals),
+                                      _stream()), "slam_fd_lbfgs_solve")
     _count()
     return loss, x, iters
 
