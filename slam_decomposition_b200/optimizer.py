@@ -151,14 +151,20 @@ class TemplateOptimizer:
         best_loss = torch.full((Nt,), float("inf"), dtype=torch.float64, device=device)
         best_k = torch.full((Nt,), -1, dtype=torch.int32, device=device)
         best_P = torch.zeros((Nt,), dtype=torch.int32, device=device)
-        best_x = None
+        # the parameter table is sized for the largest template of the range up front, so that its shape does not depend
+        # on where this rank's targets happen to be solved (ranks gather their tables with one fixed-shape collective)
+        k_list = list(k_range)
+        if not k_list:
+            raise ValueError("empty spanning range")
+        b.build(n_repetitions=max(k_list))
+        best_x = torch.zeros((Nt, b.desc.n_params), dtype=torch.float64, device=device)
         active = torch.ones((Nt,), dtype=torch.int32, device=device)
         evals = torch.zeros(1, dtype=torch.int64, device=device)
         per_k = []
         ar = ws["ar"]
         timing = engine.LBFGS_EVENTS is not None
         marks = []
-        for k in k_range:
+        for k in k_list:
             logging.info(f"Starting opt on template size {k}")
             b.build(n_repetitions=k)
             desc = b.desc
