@@ -412,6 +412,26 @@ def micro_benchmarks(engine, peak_flops):
         b.record()
         torch.cuda.synchronize()
         out[label] = {"samples_per_s": n / (a.elapsed_time(b) * 1e-3), "samples": n, "params": basis.desc.n_params}
+    # K2 on a parameter-bound smush template (parallel_drive_volume.py:175-199, sqrt(iSWAP) k=3, T=2, P=30): loss + analytic
+    # adjoint gradient through the slice exponentials vs the forward evaluation a finite-difference gradient repeats P+1 times
+    basis = pdv.smush_template(math.pi / 2, 0.0, 0.5, 3)
+    Bs = 1 << 20
+    g = torch.Generator(device=dev).manual_seed(77)
+    Xs = (torch.rand((Bs, basis.desc.n_params), device=dev, dtype=torch.float64, generator=g) - 0.5) * (8 * math.pi)
+    ls = torch.empty(Bs, device=dev, dtype=torch.float64)
+    gs = torch.empty_like(Xs)
+    for label, want in (("smush_k3_loss_grad_adjoint", True), ("smush_k3_loss_only", False)):
+        for _ in range(3):
+            engine.loss_grad(basis.desc, Xs, V, out_loss=ls, out_grad=gs if want else None, want_grad=want)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            engine.loss_grad(basis.desc, Xs, V, out_loss=ls, out_grad=gs if want else None, want_grad=want)
+        b.record()
+        torch.cuda.synchronize()
+        out[label] = {"evals_per_s": 3 * Bs / (a.elapsed_time(b) * 1e-3), "batch": Bs, "params": basis.desc.n_params}
+    out["smush_k3_adjoint_vs_fd_gradient"] = (out["smush_k3_loss_grad_adjoint"]["evals_per_s"] * (basis.desc.n_params + 1)
+                                              / out["smush_k3_loss_only"]["evals_per_s"])
     return out
 
 

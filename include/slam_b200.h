@@ -116,6 +116,10 @@ int slam_template_eval(const SlamTemplateDesc* desc, const double* x, int64_t ld
  *   loss    [dev] double[B]
  *   grad    [dev] double[B, ldg] or NULL (loss only)
  *   trace   [dev] double[B, 2]  or NULL: T = Tr(V^dag U)
+ * Templates with parameter-bound ConversionGainSmush / ConversionGainSmush1QPhase gates (hamiltonian.py:114-182) are
+ * differentiated through every time slice exp(-i dt H): Hermitian eigen-decomposition of H per slice and the
+ * Daleckii-Krein divided differences give d loss / d (amplitudes, phases, couplings, Z terms, duration) in one
+ * backward pass (one thread per row).
  */
 int slam_loss_grad(const SlamTemplateDesc* desc, const double* x, int64_t ldx, const double* V, int64_t Nt,
                    const int32_t* tgt_idx, int32_t cost_kind, double* loss, double* grad, int64_t ldg,
@@ -183,9 +187,12 @@ int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, 
  * class (scipy BFGS with jac=None: P forward differences of step 1.49e-8 per gradient, optimizer.py:270-278) for the
  * templates whose gates have no closed-form derivative here -- parameter-bound ConversionGainSmush /
  * ConversionGainSmush1QPhase gates (hamiltonian.py:114-182) -- and for BasicCostInverse x circuit_fidelity
- * (optimizer.py:200-201).  cost_kind must be trace based (BASIC, SQUARE, BASIC_INVERSE).  central != 0 selects central
- * differences (2P evaluations per gradient, step 6e-6).  Box bounds (opts->lower/upper) by projection; the trace
- * fields of opts are ignored.  Other arguments as slam_lbfgs_solve; out_evals counts forward evaluations.
+ * (optimizer.py:200-201).  cost_kind must be trace based (BASIC, SQUARE, BASIC_INVERSE).
+ *   central = 0: forward differences (scipy's jac=None);  1: central differences (2P evaluations per gradient, step 6e-6);
+ *   central = 2: ANALYTIC adjoint gradient through the smush slices (as slam_loss_grad; smush templates only, else
+ *                SLAM_ERR_UNSUPPORTED): one backward pass (~3 forward evaluations of work) instead of P + 1 evaluations.
+ * Box bounds (opts->lower/upper) by projection; the trace fields of opts are ignored.  Other arguments as
+ * slam_lbfgs_solve; out_evals counts forward evaluations (one per gradient when central = 2).
  */
 int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
                         const double* x0, int64_t ldx0, uint64_t seed, const int32_t* active,

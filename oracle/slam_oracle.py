@@ -490,12 +490,15 @@ def _du3(theta, phi, lam):
     return dth, dph, dla
 
 
-def loss_and_grad(tmpl: OracleTemplate, Xk, target_u, kind: str = "basic", h_gate: float = 1e-6):
+def loss_and_grad(tmpl: OracleTemplate, Xk, target_u, kind: str = "basic", h_gate: float = 1e-6,
+                  richardson: bool = False):
     """Loss and analytic gradient (API parameter order) by explicit derivative matrices.
 
-    1Q parameters use closed-form derivative matrices; 2Q (``Q``) parameters of closed-form gates
+    1Q parameters use closed-form derivative matrices; 2Q (``Q``) parameters
     use a central difference of the *gate matrix only* (step ``h_gate``), which is exact to O(h^2)
-    and independent of the CUDA kernel's closed-form derivative.
+    and independent of the CUDA kernels' derivatives (closed form for RiSwap / ConversionGain, Daleckii-Krein
+    through the slice exponentials for the smush gates).  ``richardson=True`` combines steps h and h/2 to O(h^4)
+    (use h_gate ~ 2e-3: truncation ~1e-12, round-off ~1e-13).
     """
     Xk = np.asarray(Xk, float)
     val = dict(zip(tmpl.names_sorted, Xk))
@@ -536,11 +539,15 @@ def loss_and_grad(tmpl: OracleTemplate, Xk, target_u, kind: str = "basic", h_gat
         else:
             for j, s in enumerate(op[2]):
                 if isinstance(s, str):
-                    vp = [val[q] if isinstance(q, str) else q for q in op[2]]
-                    vm = list(vp)
-                    vp[j] += h_gate
-                    vm[j] -= h_gate
-                    D = (tmpl._gate_matrix(vp) - tmpl._gate_matrix(vm)) / (2 * h_gate)
+                    v0 = [val[q] if isinstance(q, str) else q for q in op[2]]
+
+                    def cdiff(h):
+                        vp, vm = list(v0), list(v0)
+                        vp[j] += h
+                        vm[j] -= h
+                        return (tmpl._gate_matrix(vp) - tmpl._gate_matrix(vm)) / (2 * h)
+
+                    D = (4 * cdiff(h_gate / 2) - cdiff(h_gate)) / 3 if richardson else cdiff(h_gate)
                     dT[s] = dT.get(s, 0) + np.trace(D @ env)
     a = abs(T)
     dabs = {nm: (np.conj(T) * d).real / a for nm, d in dT.items()}

@@ -177,6 +177,9 @@ static int launch_eval(const KTemplate& kt, const double* x, int64_t ldx, double
 }
 
 int smush_eval_launch(const KTemplate& kt, const double* x, int64_t ldx, double* U, int64_t B, cudaStream_t st);
+int smush_loss_grad_launch(const KTemplate& kt, const double* x, int64_t ldx, const double* V, int64_t Nt,
+                           const int32_t* tgt_idx, int cost_kind, double* loss, double* grad, int64_t ldg, double* trace,
+                           int64_t B, cudaStream_t st);
 
 }  // namespace slam
 
@@ -214,8 +217,10 @@ extern "C" int slam_loss_grad(const SlamTemplateDesc* desc, const double* x, int
   if (!V || !loss || Nt <= 0 || (desc->n_params > 0 && !x)) return SLAM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
-  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/false);
+  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true);
   if (rc != SLAM_OK) return rc;
+  if (kt.gmode == GM_SMUSH)  // parameter-bound smush gates: thread-per-row adjoint through the slice exponentials
+    return smush_loss_grad_launch(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, st);
   if (kt.gmode == GM_DENSE && desc->gate_kind != SLAM_GATE_FIXED) {
     rc = lower_const_smush(desc, &kt, st);
     if (rc != SLAM_OK) return rc;

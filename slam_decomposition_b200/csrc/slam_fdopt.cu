@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "slam_host.h"
+#include "slam_adj1.cuh"
 #include "slam_objective.cuh"
 #include "slam_philox.cuh"
 
@@ -58,6 +59,9 @@ struct ShiftedParams {
   }
 };
 
+// MODE 0: forward differences (scipy's jac=None), 1: central differences, 2: analytic adjoint gradient through the
+// smush slices (slam_adj1.cuh; GM_SMUSH templates only) -- one backward pass instead of P + 1 forward evaluations
+template <int MODE>
 __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ FdArgs A, const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
   const int m = kFdHist;
@@ -96,9 +100,18 @@ __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ F
     // gradient of buffer xb into buffer gb (fx = objective at xb); returns max |projected g|
     auto grad_at = [&](int xb, int gb, double fx) -> double {
       double gmax = 0.0;
+      if (MODE == 2) {
+        StridedParams ps{&vec(xb, 0), T};
+        StridedGrad gsw{&vec(gb, 0), T};
+        for (int j = 0; j < n; ++j) vec(gb, j) = 0.0;
+        adj1_loss_grad(kt, ps, A.V + t * 32, A.cost_kind, gsw, nullptr);
+        ++evals;
+      }
       for (int j = 0; j < n; ++j) {
         double gj;
-        if (A.central) {
+        if (MODE == 2) {
+          gj = vec(gb, j);
+        } else if (MODE == 1) {
           ShiftedParams pp{&vec(xb, 0), T, j, h_cen}, pm{&vec(xb, 0), T, j, -h_cen};
           gj = (objective_value(kt, pp, ti, A.cost_kind) - objective_value(kt, pm, ti, A.cost_kind)) / (2.0 * h_cen);
           evals += 2;
@@ -107,7 +120,7 @@ __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ F
           gj = (objective_value(kt, pp, ti, A.cost_kind) - fx) / h_fwd;
           ++evals;
         }
-        vec(gb, j) = gj;
+        if (MODE != 2) vec(gb, j) = gj;
         double gp = gj;
         if (A.lower) {
           const double xj = vec(xb, j);
@@ -289,12 +302,13 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   if (x0 && ldx0 < desc->n_params) return SLAM_ERR_INVALID;
   if (opts->cost_kind != SLAM_COST_BASIC && opts->cost_kind != SLAM_COST_SQUARE && opts->cost_kind != SLAM_COST_BASIC_INVERSE)
     return SLAM_ERR_UNSUPPORTED;  // the coordinate-based functionals are piecewise constant (8-dp rounding): no gradient
-  if (opts->max_iter < 1 || desc->n_params < 1) return SLAM_ERR_INVALID;
+  if (opts->max_iter < 1 || desc->n_params < 1 || central < 0 || central > 2) return SLAM_ERR_INVALID;
   if (Nt == 0) return SLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
   int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true);
   if (rc != SLAM_OK) return rc;
+  if (central == 2 && kt.gmode != GM_SMUSH) return SLAM_ERR_UNSUPPORTED;  // closed-form gates: slam_lbfgs_solve
   if (kt.gmode == GM_DENSE && desc->gate_kind != SLAM_GATE_FIXED) {
     rc = lower_const_smush(desc, &kt, st);
     if (rc != SLAM_OK) return rc;
@@ -322,7 +336,9 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
 
   FdArgs A;
   A.V = V; A.x0 = x0; A.ldx0 = ldx0; A.seed = seed; A.active = active; A.Nt = Nt; A.restarts = restarts;
-  A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit; A.central = central ? 1 : 0;
+  A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit; A.central = central;
+  // smush gates carry no circuit_fidelity factor, so 1 - BasicCostInverse x 1 is BasicCost (optimizer.py:200-201)
+  if (central == 2 && A.cost_kind == SLAM_COST_BASIC_INVERSE) A.cost_kind = SLAM_COST_BASIC;
   { const char* dbg = getenv("SLAM_B200_FD_DEBUG"); A.debug = (dbg && dbg[0] == '1') ? 1 : 0; }
   A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
@@ -330,7 +346,9 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   A.upper = A.lower ? opts->upper : nullptr;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved; A.ws = ws; A.T = T;
-  fd_lbfgs_kernel<<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+  if (central == 2) fd_lbfgs_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+  else if (central == 1) fd_lbfgs_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+  else fd_lbfgs_kernel<0><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(next, st);
   cudaFreeAsync(solved, st);

@@ -1,6 +1,6 @@
 // slam_smush.cu -- K4: templates whose 2Q gate is a time-sliced smush Hamiltonian (forward evaluation),
 // constant-gate lowering, and K4b: the parallel-drive Weyl trajectory.
-#include "slam_fwd1.cuh"
+#include "slam_adj1.cuh"
 #include "slam_host.h"
 #include "slam_weyl.cuh"
 
@@ -24,6 +24,47 @@ __global__ void __launch_bounds__(128) smush_eval_kernel(const double* __restric
 int smush_eval_launch(const KTemplate& kt, const double* x, int64_t ldx, double* U, int64_t B, cudaStream_t st) {
   const unsigned grid = (unsigned)((B + 127) / 128);
   smush_eval_kernel<<<grid, 128, 0, st>>>(x, ldx, U, B, kt);
+  SLAM_CUDA_CHECK(cudaGetLastError());
+  return SLAM_OK;
+}
+
+// ---- K2 for parameter-bound smush templates: loss + analytic adjoint gradient, one thread per row -------
+// (replaces objective_func + scipy's (P+1)-evaluation finite-difference gradient for these templates,
+//  optimizer.py:191-214, 270-278)
+template <bool WANT_GRAD>
+__global__ void __launch_bounds__(128)
+smush_loss_grad_kernel(const double* __restrict__ x, int64_t ldx, const double* __restrict__ V, int64_t Nt,
+                       const int32_t* __restrict__ tgt_idx, int cost_kind, double* __restrict__ loss,
+                       double* __restrict__ grad, int64_t ldg, double* __restrict__ trace, int64_t B,
+                       const __grid_constant__ KTemplate kt) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t tgt = tgt_idx ? (int64_t)tgt_idx[b] : (b % Nt);
+  GlobalParams ps{x + b * ldx};
+  cd T;
+  double l;
+  if (WANT_GRAD) {
+    RowGrad gs{grad + b * ldg};
+    for (int j = 0; j < kt.P; ++j) gs.row[j] = 0.0;  // parameters bound to no slot keep a zero derivative
+    l = adj1_loss_grad(kt, ps, V + tgt * 32, cost_kind, gs, &T);
+  } else {
+    l = fwd1_loss(kt, ps, V + tgt * 32, cost_kind, &T);
+  }
+  loss[b] = l;
+  if (trace) {
+    trace[2 * b] = T.re;
+    trace[2 * b + 1] = T.im;
+  }
+}
+
+int smush_loss_grad_launch(const KTemplate& kt, const double* x, int64_t ldx, const double* V, int64_t Nt,
+                           const int32_t* tgt_idx, int cost_kind, double* loss, double* grad, int64_t ldg, double* trace,
+                           int64_t B, cudaStream_t st) {
+  const unsigned grid = (unsigned)((B + 127) / 128);
+  if (grad)
+    smush_loss_grad_kernel<true><<<grid, 128, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, kt);
+  else
+    smush_loss_grad_kernel<false><<<grid, 128, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, nullptr, 0, trace, B, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }

@@ -166,9 +166,12 @@ def lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: Sl
 
 def fd_lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: SlamOptOpts,
                    x0: Optional[torch.Tensor] = None, seed: int = 0, active: Optional[torch.Tensor] = None,
-                   evals: Optional[torch.Tensor] = None, out: Optional[tuple] = None, central: bool = False):
-    """K5c: batched L-BFGS with finite-difference gradients over the generic forward objective (parameter-bound smush
-    gates, BasicCostInverse).  Returns (loss [Nt,R], x [Nt,R,P], iters [Nt,R]); `evals` counts forward evaluations."""
+                   evals: Optional[torch.Tensor] = None, out: Optional[tuple] = None, central=False):
+    """K5c: batched L-BFGS over the generic forward objective (parameter-bound smush gates, BasicCostInverse).
+    `central`: False / 0 = forward differences (scipy's jac=None), True / 1 = central differences, 2 or "adjoint" =
+    analytic adjoint gradient through the smush slices (smush templates only).  Returns (loss [Nt,R], x [Nt,R,P],
+    iters [Nt,R]); `evals` counts forward evaluations (one per gradient in adjoint mode)."""
+    mode = 2 if central == "adjoint" else int(central)
     V = _dev(V, torch.complex128, "V")
     Nt = V.shape[0]
     P = desc.n_params
@@ -190,7 +193,7 @@ def fd_lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts:
     with torch.cuda.device(V.device):
         lib = _enter(V)
         check(lib.slam_fd_lbfgs_solve(C.byref(desc), _ptr(V), Nt, int(restarts), _ptr(x0), P, C.c_uint64(seed), _ptr(active),
-                                      C.byref(opts), int(bool(central)), _ptr(loss), _ptr(x), _ptr(iters), _ptr(evals),
+                                      C.byref(opts), mode, _ptr(loss), _ptr(x), _ptr(iters), _ptr(evals),
                                       _stream()), "slam_fd_lbfgs_solve")
     _count()
     return loss, x, iters

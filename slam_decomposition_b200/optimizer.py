@@ -46,7 +46,8 @@ class TemplateOptimizer:
         assert not (self.preseeding and self.basis.n_qubits != 2)
         self.last_stats = {}
         self._ws = None
-        self.fd_central = True  # K5c: central differences (False = scipy's forward differences, step 1.49e-8)
+        self.fd_central = True  # K5c without an adjoint: central differences (False = scipy's forward differences, step 1.49e-8)
+        self.smush_adjoint = True  # K5c on parameter-bound smush templates: analytic adjoint gradient (False = differences)
         self._host_x = None  # pinned staging buffer of approximate_targets()
         self.launch_evals = []  # (k, loss+grad evaluations) per slam_lbfgs_solve launch while engine.LBFGS_EVENTS is on
 
@@ -92,8 +93,9 @@ class TemplateOptimizer:
         (optimizer.py:255-268).  Here:
           "lbfgs"  analytic-gradient L-BFGS (K5) whenever the functional is BasicCost / SquareCost and every gate has a
                    closed-form derivative;
-          "fd"     L-BFGS with finite-difference gradients over the generic forward evaluator (K5c) -- the reference's own
-                   algorithm class -- for parameter-bound smush gates and BasicCostInverse;
+          "fd"     thread-per-problem L-BFGS over the generic forward evaluator (K5c) for parameter-bound smush gates and
+                   BasicCostInverse: analytic adjoint gradients through the slice exponentials for smush templates
+                   (`smush_adjoint`), finite differences -- the reference's own algorithm class -- otherwise;
           "nm"     the derivative-free Nelder-Mead kernel (K5b) for the coordinate-based functionals (Makhlin / Weyl /
                    reduced: piecewise constant after the 8-dp rounding), and when override_method asks for it."""
         if self.override_method == "Nelder-Mead":
@@ -219,8 +221,11 @@ class TemplateOptimizer:
                 # progress per 32 steps; the others run on to opts.gtol / f_stop with central differences.
                 saved = (opts.cost_kind, opts.f_far)
                 opts.cost_kind, opts.f_far = ck, max(opts.f_far, 1e-4)
+                is_smush = (desc.gate_kind in (_lib.GATE_SMUSH, _lib.GATE_SMUSH_1QPHASE)
+                            and any(desc.slot_param[g][s] >= 0 for g in range(desc.k) for s in range(desc.n_slots)))
+                mode = 2 if (is_smush and self.smush_adjoint) else int(bool(self.fd_central))
                 loss, x, iters = engine.fd_lbfgs_solve(desc, V, R, opts, x0=x0, seed=seed, active=active, evals=evals,
-                                                       out=(ws["loss"], x, ws["iters"]), central=self.fd_central)
+                                                       out=(ws["loss"], x, ws["iters"]), central=mode)
                 opts.cost_kind, opts.f_far = saved
             else:
                 loss, x, iters = engine.lbfgs_solve(desc, V, R, opts, x0=x0, seed=seed, active=active, evals=evals,
