@@ -45,7 +45,7 @@ __device__ __forceinline__ void herm_eig4(HermG& A, cd Q[4][4]) {
     for (int e = 0; e < 6; ++e) off = fma(A.u[e].re, A.u[e].re, fma(A.u[e].im, A.u[e].im, off));
 #pragma unroll
     for (int i = 0; i < 4; ++i) tot = fma(A.d[i], A.d[i], tot);
-    if (off <= 1e-33 * (tot + off)) break;
+    if (off <= 1e-30 * (tot + off)) break;  // above the round-off floor (~1e-32 ||A||_F^2), so the test always fires
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll

@@ -6,6 +6,9 @@
 //   -> Weyl coordinates (joint Jacobi) -> fold c1 -> bin -> one 64-bit atomic per sample.
 // Nothing but the histogram (and, optionally, the coordinates) is written to HBM; there is no parameter
 // array at all.  The RNG is counter-based, so a rank regenerates exactly its own [first, first+n) slice.
+#include <algorithm>
+#include <cstdlib>
+
 #include "slam_fwd1.cuh"
 #include "slam_host.h"
 #include "slam_philox.cuh"
@@ -19,15 +22,17 @@ struct PhiloxParams {
   __device__ __forceinline__ double get(int j) const { return philox_param(seed, sample, j, lo, span); }
 };
 
-__global__ void __launch_bounds__(128) coverage_kernel(uint64_t seed, int64_t first, int64_t n, double lo, double span,
-                                                       int nbins, unsigned long long* __restrict__ hist,
-                                                       double* __restrict__ coords, const __grid_constant__ KTemplate kt) {
+// GMT: gate mode fixed at compile time (-1 = runtime dispatch); MINB: resident CTAs per SM the register allocation targets
+template <int GMT, int MINB>
+__global__ void __launch_bounds__(128, MINB) coverage_kernel(uint64_t seed, int64_t first, int64_t n, double lo, double span,
+                                                             int nbins, unsigned long long* __restrict__ hist,
+                                                             double* __restrict__ coords, const __grid_constant__ KTemplate kt) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const double scale = 2.0 * (double)nbins;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     PhiloxParams ps{seed, (uint64_t)(first + i), lo, span};
     cd R[4][4];
-    fwd1_chain(kt, ps, R);
+    fwd1_chain<PhiloxParams, GMT>(kt, ps, R);
     cd M[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
@@ -47,6 +52,16 @@ __global__ void __launch_bounds__(128) coverage_kernel(uint64_t seed, int64_t fi
       atomicAdd(hist + ((size_t)b0 * nbins + b1) * nbins + b2, 1ULL);
     }
   }
+}
+
+template <int GMT, int MINB>
+static int launch_coverage(const KTemplate& kt, uint64_t seed, int64_t first, int64_t n, double lo, double span, int nbins,
+                           unsigned long long* hist, double* coords, int sms, cudaStream_t st) {
+  const int64_t want = (n + 127) / 128;
+  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 8 * MINB);  // grid-stride, a multiple of the SM count
+  coverage_kernel<GMT, MINB><<<grid, 128, 0, st>>>(seed, first, n, lo, span, nbins, hist, coords, kt);
+  SLAM_CUDA_CHECK(cudaGetLastError());
+  return SLAM_OK;
 }
 
 }  // namespace slam
@@ -69,9 +84,31 @@ extern "C" int slam_coverage_mc(const SlamTemplateDesc* desc, uint64_t seed, int
   int dev = 0, sms = 0;
   SLAM_CUDA_CHECK(cudaGetDevice(&dev));
   SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t want = (n_samples + 127) / 128;
-  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 16);  // grid-stride, a multiple of the SM count
-  coverage_kernel<<<grid, 128, 0, st>>>(seed, first_sample, n_samples, lo, hi - lo, nbins, hist, coords, kt);
-  SLAM_CUDA_CHECK(cudaGetLastError());
+  const double span = hi - lo;
+  // Resident CTAs per SM the kernels are compiled for (register cap 255 / 168 / 128).  Measured on B200, Msamples/s at
+  // 2 / 3 / 4 CTAs: sqrt(iSWAP) k=3 plain 1610 / 1936 / 2134, CNOT k=3 plain 1499 / 1852 / 2066, sqrt(iSWAP) k=3 smush
+  // 324 / 332 / 347 (scripts/cov_ab.py): the chains are latency bound, so 16 warps/SM win despite 160-1000 B of spills.
+  const char* e = getenv("SLAM_B200_COV_MINB");
+  const int minb = e ? atoi(e) : 0;
+#define SLAM_COV(GM, MB) return launch_coverage<GM, MB>(kt, seed, first_sample, n_samples, lo, span, nbins, hist, coords, sms, st)
+  switch (kt.gmode) {
+    case GM_SYM:
+      if (minb == 2) SLAM_COV(GM_SYM, 2);
+      if (minb == 3) SLAM_COV(GM_SYM, 3);
+      SLAM_COV(GM_SYM, 4);
+    case GM_BLOCK:
+      if (minb == 2) SLAM_COV(GM_BLOCK, 2);
+      if (minb == 3) SLAM_COV(GM_BLOCK, 3);
+      SLAM_COV(GM_BLOCK, 4);
+    case GM_DENSE:
+      if (minb == 2) SLAM_COV(GM_DENSE, 2);
+      if (minb == 3) SLAM_COV(GM_DENSE, 3);
+      SLAM_COV(GM_DENSE, 4);
+    default:
+      if (minb == 2) SLAM_COV(GM_SMUSH, 2);
+      if (minb == 3) SLAM_COV(GM_SMUSH, 3);
+      SLAM_COV(GM_SMUSH, 4);
+  }
+#undef SLAM_COV
   return SLAM_OK;
 }

@@ -273,12 +273,14 @@ __device__ __forceinline__ void fwd1_layer(const KTemplate& kt, const PS& ps, in
   }
 }
 
-template <class PS>
+// GMT >= 0 fixes the gate mode at compile time (the other modes' code is not generated); -1 = runtime dispatch on kt.gmode
+template <class PS, int GMT = -1>
 __device__ __forceinline__ void fwd1_gate(const KTemplate& kt, const PS& ps, int g, cd R[4][4]) {
-  if (kt.gmode == GM_SYM) {
+  const int gmode = (GMT >= 0) ? GMT : kt.gmode;
+  if (gmode == GM_SYM) {
 #pragma unroll
     for (int col = 0; col < 4; ++col) sym_apply<OP_N>(R[col], kt.gsym[g][0], kt.gsym[g][1], kt.gsym[g][2], kt.gsym[g][3]);
-  } else if (kt.gmode == GM_BLOCK) {
+  } else if (gmode == GM_BLOCK) {
     BlockGate bg;
     if (kt.gate_bound[g]) {
       double2 q[4] = {make_double2(1, 0), make_double2(1, 0), make_double2(1, 0), make_double2(1, 0)};
@@ -300,7 +302,7 @@ __device__ __forceinline__ void fwd1_gate(const KTemplate& kt, const PS& ps, int
     }
 #pragma unroll
     for (int col = 0; col < 4; ++col) block_apply<OP_N>(R[col], bg);
-  } else if (kt.gmode == GM_DENSE) {
+  } else if (gmode == GM_DENSE) {
 #pragma unroll
     for (int col = 0; col < 4; ++col) dense_apply<OP_N>(R[col], kt.dense[g]);
   } else {  // GM_SMUSH
@@ -323,7 +325,7 @@ __device__ __forceinline__ void fwd1_gate(const KTemplate& kt, const PS& ps, int
   }
 }
 
-template <class PS>
+template <class PS, int GMT = -1>
 __device__ __forceinline__ void fwd1_chain(const KTemplate& kt, const PS& ps, cd R[4][4]) {
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -331,7 +333,7 @@ __device__ __forceinline__ void fwd1_chain(const KTemplate& kt, const PS& ps, cd
     for (int r = 0; r < 4; ++r) R[c][r] = mkc(c == r ? 1.0 : 0.0, 0.0);
   for (int i = 0; i <= kt.k; ++i) {
     fwd1_layer(kt, ps, i, R);
-    if (i < kt.k) fwd1_gate(kt, ps, i, R);
+    if (i < kt.k) fwd1_gate<PS, GMT>(kt, ps, i, R);
   }
 }
 
