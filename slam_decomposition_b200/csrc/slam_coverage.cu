@@ -16,10 +16,12 @@
 
 namespace slam {
 
-struct PhiloxParams {
-  uint64_t seed, sample;
-  double lo, span;
-  __device__ __forceinline__ double get(int j) const { return philox_param(seed, sample, j, lo, span); }
+// The sample's P parameters are generated once, two per Philox block, into the thread's column of a shared-memory
+// table (entry j of thread t at xs[j * 128 + t]: conflict-free) and read from there by the chain.  Calling the generator
+// per parameter access ran every Philox block twice; at P = 12 that was a third of the kernel's instructions.
+struct StagedParams {
+  const double* col;
+  __device__ __forceinline__ double get(int j) const { return col[j * 128]; }
 };
 
 // GMT: gate mode fixed at compile time (-1 = runtime dispatch); MINB: resident CTAs per SM the register allocation targets
@@ -27,12 +29,21 @@ template <int GMT, int MINB>
 __global__ void __launch_bounds__(128, MINB) coverage_kernel(uint64_t seed, int64_t first, int64_t n, double lo, double span,
                                                              int nbins, unsigned long long* __restrict__ hist,
                                                              double* __restrict__ coords, const __grid_constant__ KTemplate kt) {
+  extern __shared__ double xs[];
+  double* col = xs + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const double scale = 2.0 * (double)nbins;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    PhiloxParams ps{seed, (uint64_t)(first + i), lo, span};
+    for (int jj = 0; 2 * jj < kt.P; ++jj) {
+      double u0, u1;
+      philox_u53_pair(seed, (uint64_t)(first + i), jj, &u0, &u1);
+      // lo + span * u with a separate multiply and add (numpy does not fuse; keeps the stream bit-identical)
+      col[(2 * jj) * 128] = __dadd_rn(lo, __dmul_rn(span, u0));
+      if (2 * jj + 1 < kt.P) col[(2 * jj + 1) * 128] = __dadd_rn(lo, __dmul_rn(span, u1));
+    }
+    StagedParams ps{col};
     cd R[4][4];
-    fwd1_chain<PhiloxParams, GMT>(kt, ps, R);
+    fwd1_chain<StagedParams, GMT>(kt, ps, R);
     cd M[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
@@ -59,7 +70,10 @@ static int launch_coverage(const KTemplate& kt, uint64_t seed, int64_t first, in
                            unsigned long long* hist, double* coords, int sms, cudaStream_t st) {
   const int64_t want = (n + 127) / 128;
   const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 8 * MINB);  // grid-stride, a multiple of the SM count
-  coverage_kernel<GMT, MINB><<<grid, 128, 0, st>>>(seed, first, n, lo, span, nbins, hist, coords, kt);
+  const size_t smem = (size_t)std::max(kt.P, 1) * 128 * sizeof(double);
+  auto kern = coverage_kernel<GMT, MINB>;
+  if (smem > 48 * 1024) SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, 128, smem, st>>>(seed, first, n, lo, span, nbins, hist, coords, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }

@@ -40,6 +40,14 @@ __device__ __forceinline__ double philox_u53(uint64_t seed, uint64_t sample, int
   return (j & 1) ? u53(c[2], c[3]) : u53(c[0], c[1]);
 }
 
+// both uniforms of the Philox block that serves parameters 2*jj and 2*jj + 1
+__device__ __forceinline__ void philox_u53_pair(uint64_t seed, uint64_t sample, int jj, double* u0, double* u1) {
+  uint32_t c[4] = {(uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)jj, kPhiloxTag};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  *u0 = u53(c[0], c[1]);
+  *u1 = u53(c[2], c[3]);
+}
+
 // lo + span*u with a separate multiply and add (numpy does not fuse; keeps the stream bit-identical)
 __device__ __forceinline__ double philox_param(uint64_t seed, uint64_t sample, int j, double lo, double span) {
   return __dadd_rn(lo, __dmul_rn(span, philox_u53(seed, sample, j)));
