@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SLAM_ABI_VERSION 1
+#define SLAM_ABI_VERSION 2
 #define SLAM_MAX_K 8      /* max 2Q-gate applications per template (reference uses <= 6)       */
 #define SLAM_MAX_SLOTS 40 /* max scalar slots of one 2Q gate (smush1q: 8 + 2T + 1, T <= 15)    */
 #define SLAM_MAX_PARAMS 256
@@ -164,6 +164,18 @@ typedef struct SlamOptOpts {
      switch to scipy L-BFGS-B when basis.using_bounds (optimizer.py:257-258, basisv2.py:174-190); +-inf allowed.   */
   const double* lower;
   const double* upper;
+  /* optional chaining of launches over ascending template sizes k (slam_lbfgs_solve only), so that the launch for k+1 can
+     be enqueued on a second stream while the launch for k drains and its CTAs fill the SMs the tail of k leaves idle:
+       solved_out [dev] int32[Nt], zeroed by the caller: flag t is set when a restart of target t ends below
+                  success_threshold in THIS launch, or when t was skipped because of solved_in (flags are cumulative);
+                  NULL = internal scratch.  Requires early_exit = 1.
+       solved_in  [dev] int32[Nt] or NULL: the solved_out array of the launch for the previous size; it may still be
+                  written while this launch runs.  Targets flagged there when one of their restarts is fetched are skipped
+                  (out_loss = DBL_MAX), which reproduces the k-loop early exit of optimizer.py:297-303 without a host
+                  round trip.  A target whose last restarts at size k succeed after size k+1 has started on it costs
+                  wasted work only: the caller keeps the smallest successful k.                                       */
+  const int32_t* solved_in;
+  int32_t* solved_out;
 } SlamOptOpts;
 
 void slam_opt_defaults(SlamOptOpts* o);

@@ -57,6 +57,8 @@ class SlamOptOpts(C.Structure):
         ("trace_x", C.c_void_p),
         ("lower", C.c_void_p),
         ("upper", C.c_void_p),
+        ("solved_in", C.c_void_p),
+        ("solved_out", C.c_void_p),
     ]
 
 
@@ -124,7 +126,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.slam_abi_version() != 1:
+    if lib.slam_abi_version() != 2:
         raise SlamError("libslam_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

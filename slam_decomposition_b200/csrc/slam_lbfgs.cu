@@ -75,6 +75,8 @@ extern "C" void slam_opt_defaults(SlamOptOpts* o) {
   o->trace_x = nullptr;
   o->lower = nullptr;
   o->upper = nullptr;
+  o->solved_in = nullptr;
+  o->solved_out = nullptr;
 }
 
 extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
@@ -86,6 +88,8 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   if (opts->cost_kind != SLAM_COST_BASIC && opts->cost_kind != SLAM_COST_SQUARE) return SLAM_ERR_UNSUPPORTED;
   if (opts->max_iter < 1 || opts->history < 0 || opts->history > kMaxHist) return SLAM_ERR_INVALID;
   if (desc->n_params < 1) return SLAM_ERR_INVALID;
+  if ((opts->solved_in || opts->solved_out) && !opts->early_exit) return SLAM_ERR_INVALID;
+  if (opts->solved_in && !opts->solved_out) return SLAM_ERR_INVALID;  // the chain needs somewhere to propagate to
   if (Nt == 0) return SLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
@@ -149,9 +153,13 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   unsigned long long* next = nullptr;
   int32_t* solved = nullptr;
   SLAM_CUDA_CHECK(cudaMallocAsync((void**)&next, sizeof(unsigned long long), st));
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&solved, sizeof(int32_t) * (size_t)Nt, st));
   SLAM_CUDA_CHECK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
-  SLAM_CUDA_CHECK(cudaMemsetAsync(solved, 0, sizeof(int32_t) * (size_t)Nt, st));
+  if (opts->solved_out) {
+    solved = opts->solved_out;  // caller-owned (and caller-zeroed) flags of a chained launch
+  } else {
+    SLAM_CUDA_CHECK(cudaMallocAsync((void**)&solved, sizeof(int32_t) * (size_t)Nt, st));
+    SLAM_CUDA_CHECK(cudaMemsetAsync(solved, 0, sizeof(int32_t) * (size_t)Nt, st));
+  }
 
   LbfgsArgs A;
   A.V = V; A.x0 = x0; A.ldx0 = ldx0; A.seed = seed; A.active = active; A.Nt = Nt; A.restarts = restarts;
@@ -163,7 +171,7 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   A.lower = (opts->lower && opts->upper) ? opts->lower : nullptr;
   A.upper = A.lower ? opts->upper : nullptr;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
-  A.next = next; A.solved = solved;
+  A.next = next; A.solved = solved; A.solved_in = opts->solved_in;
 
   const int64_t total = Nt * (int64_t)restarts;
   cfg.grid = (int)std::min<int64_t>((int64_t)sms, (total + teams - 1) / teams);
@@ -176,6 +184,6 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
     default: rc = SLAM_ERR_UNSUPPORTED;
   }
   cudaFreeAsync(next, st);
-  cudaFreeAsync(solved, st);
+  if (!opts->solved_out) cudaFreeAsync(solved, st);
   return rc;
 }

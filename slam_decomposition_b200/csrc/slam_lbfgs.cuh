@@ -54,6 +54,7 @@ struct LbfgsArgs {
   unsigned long long* out_evals;
   unsigned long long* next;  // work counter
   int32_t* solved;           // per-target flag (early exit)
+  const int32_t* solved_in;  // flags of the launch for the previous template size (may still be written), or null
 };
 
 // launch configuration chosen on the host (slam_lbfgs.cu)
@@ -164,6 +165,10 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
           pid = t * A.restarts + r_idx;  // index of the (target, restart) pair in the output tables / the x0 stream
           tgt = t;
           bool skip = A.active && A.active[t] == 0;
+          if (!skip && A.solved_in && *((volatile const int32_t*)(A.solved_in + t)) != 0) {
+            skip = true;  // solved at a smaller template size: propagate, so that the flags stay cumulative
+            if (sub == 0) A.solved[t] = 1;
+          }
           if (!skip && A.early_exit) skip = *((volatile int32_t*)(A.solved + t)) != 0;
           if (skip) {
             if (sub == 0) {

@@ -23,6 +23,8 @@ __all__ = [
 LAUNCHES = 0
 # when set to a list, lbfgs_solve appends (k, start_event, end_event) for per-launch device timing
 LBFGS_EVENTS = None
+# bench.py instrumentation for the chained (two-stream) sweep: (start, end) CUDA events around the whole launch chain
+LBFGS_SPANS = None
 
 
 def _count(n: int = 1) -> None:

@@ -11,6 +11,7 @@ Return contract kept (optimizer.py:186): ``(training_loss, coordinate
 from __future__ import annotations
 
 import logging
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -48,6 +49,10 @@ class TemplateOptimizer:
         self._ws = None
         self.fd_central = True  # K5c without an adjoint: central differences (False = scipy's forward differences, step 1.49e-8)
         self.smush_adjoint = True  # K5c on parameter-bound smush templates: analytic adjoint gradient (False = differences)
+        # K5 launches of consecutive template sizes are chained on two streams (SlamOptOpts.solved_in / solved_out) so the
+        # next size fills the SMs the tail of the current one leaves idle and no host round trip separates them
+        self.pipeline = os.environ.get("SLAM_B200_PIPELINE", "1") != "0"
+        self._pipe = None  # streams + per-size workspaces of the chained sweep
         self._host_x = None  # pinned staging buffer of approximate_targets()
         self.launch_evals = []  # (k, loss+grad evaluations) per slam_lbfgs_solve launch while engine.LBFGS_EVENTS is on
 
@@ -142,6 +147,12 @@ class TemplateOptimizer:
         opts.cost_kind = ck if ck in (_lib.COST_BASIC, _lib.COST_SQUARE) else _lib.COST_BASIC
         opts.success_threshold = float(self.success_threshold)
         opts.f_stop = min(opts.f_stop, 1e-3 * float(self.success_threshold))
+        k_list = list(k_range)
+        if not k_list:
+            raise ValueError("empty spanning range")
+        if (self.pipeline and not keep_history and opts.early_exit and len(k_list) > 1
+                and not getattr(b, "using_bounds", False) and self._all_lbfgs(k_list, ck)):
+            return self._run_chained(V, k_list, opts)
         # persistent workspace: output tables are reused across k and across calls (no allocator churn per sweep)
         ws = self._ws
         if ws is None or ws["key"] != (Nt, R, str(device)):
@@ -155,9 +166,6 @@ class TemplateOptimizer:
         best_P = torch.zeros((Nt,), dtype=torch.int32, device=device)
         # the parameter table is sized for the largest template of the range up front, so that its shape does not depend
         # on where this rank's targets happen to be solved (ranks gather their tables with one fixed-shape collective)
-        k_list = list(k_range)
-        if not k_list:
-            raise ValueError("empty spanning range")
         b.build(n_repetitions=max(k_list))
         best_x = torch.zeros((Nt, b.desc.n_params), dtype=torch.float64, device=device)
         active = torch.ones((Nt,), dtype=torch.int32, device=device)
@@ -263,6 +271,102 @@ class TemplateOptimizer:
             prev = cur_
         return {"best_loss": best_loss.cpu().numpy(), "best_k": best_k.cpu().numpy(), "best_P": best_P.cpu().numpy(),
                 "best_x": best_x, "per_k": per_k, "best_loss_dev": best_loss, "best_k_dev": best_k}
+
+    # ------------------------------------------------------------------------------------------
+    # chained sweep: one K5 launch per template size, alternating between two streams
+    # ------------------------------------------------------------------------------------------
+    def _all_lbfgs(self, k_list, ck) -> bool:
+        b = self.basis
+        for k in k_list:
+            b.build(n_repetitions=k)
+            if self._solver(b.desc, ck) != "lbfgs":
+                return False
+        return True
+
+    def _run_chained(self, V: torch.Tensor, k_list, opts) -> dict:
+        """The k-loop of optimizer.py:233-303 without host round trips.  Every size gets its own result tables; the launch
+        for size k_{i+1} reads the (live) solved flags of size k_i and skips the targets already below the threshold, which
+        is the reference's early exit; launches alternate between two streams, so the CTAs of the next size start on the SMs
+        the draining launch frees.  The merge afterwards keeps, per target, the smallest size that succeeded (else the lowest
+        loss seen), exactly what the sequential loop keeps."""
+        b = self.basis
+        device = V.device
+        Nt = V.shape[0]
+        R = int(self.training_restarts)
+        thr = float(self.success_threshold)
+        main = torch.cuda.current_stream(device)
+        descs = []
+        for k in k_list:
+            b.build(n_repetitions=k)
+            descs.append((k, b.desc, b.desc.n_params))
+        Pmax = max(P for _, _, P in descs)
+        key = (Nt, R, str(device), tuple((k, P) for k, _, P in descs))
+        pipe = self._pipe
+        if pipe is None or pipe["key"] != key:
+            pipe = {"key": key, "streams": (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)),
+                    "flags": torch.empty((len(descs), Nt), dtype=torch.int32, device=device),
+                    "evals": torch.empty(len(descs), dtype=torch.int64, device=device),
+                    "ar": torch.arange(Nt, device=device),
+                    "tab": [{"loss": torch.empty((Nt, R), dtype=torch.float64, device=device),
+                             "iters": torch.empty((Nt, R), dtype=torch.int32, device=device),
+                             "x": torch.empty((Nt, R, P), dtype=torch.float64, device=device)} for _, _, P in descs]}
+            self._pipe = pipe
+        flags, evals, ar = pipe["flags"], pipe["evals"], pipe["ar"]
+        flags.zero_()
+        evals.zero_()
+        timing = engine.LBFGS_EVENTS is not None
+        span = None
+        if engine.LBFGS_SPANS is not None:
+            span = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            span[0].record(main)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        reduced = []
+        for i, (k, desc, P) in enumerate(descs):
+            logging.info(f"Starting opt on template size {k}")
+            st = pipe["streams"][i % 2]
+            st.wait_event(ready)
+            tab = pipe["tab"][i]
+            with torch.cuda.stream(st):
+                x0, lo, hi = self._x0(Nt, device)
+                o = _lib.SlamOptOpts.from_buffer_copy(opts)
+                o.x0_lo, o.x0_hi = lo, hi
+                o.lower, o.upper = None, None
+                o.trace_cap, o.trace_loss, o.trace_x = 0, None, None
+                o.solved_in = flags[i - 1].data_ptr() if i > 0 else None
+                o.solved_out = flags[i].data_ptr()
+                seed = int(np.random.randint(0, 2 ** 62))
+                loss, x, _ = engine.lbfgs_solve(desc, V, R, o, x0=x0, seed=seed, active=None, evals=evals[i:i + 1],
+                                                out=(tab["loss"], tab["x"], tab["iters"]))
+                lmin, rmin = loss.min(dim=1)
+                reduced.append((k, P, lmin, x[ar, rmin]))
+        for st in pipe["streams"]:
+            main.wait_stream(st)
+        if span is not None:
+            span[1].record(main)
+            engine.LBFGS_SPANS.append(span)
+        # merge (main stream): sizes ascending, a target stops taking part once it is below the threshold
+        best_loss = torch.full((Nt,), float("inf"), dtype=torch.float64, device=device)
+        best_k = torch.full((Nt,), -1, dtype=torch.int32, device=device)
+        best_P = torch.zeros((Nt,), dtype=torch.int32, device=device)
+        best_x = torch.zeros((Nt, max(Pmax, descs[-1][2])), dtype=torch.float64, device=device)
+        active = torch.ones((Nt,), dtype=torch.bool, device=device)
+        for k, P, lmin, xsel in reduced:
+            improved = active & (lmin < best_loss)
+            best_x[:, :P] = torch.where(improved[:, None], xsel, best_x[:, :P])
+            if best_x.shape[1] > P:
+                best_x[:, P:] = torch.where(improved[:, None], torch.zeros_like(best_x[:, P:]), best_x[:, P:])
+            best_loss = torch.where(improved, lmin, best_loss)
+            best_k = torch.where(improved, torch.full_like(best_k, k), best_k)
+            best_P = torch.where(improved, torch.full_like(best_P, P), best_P)
+            active = active & ~(best_loss < thr)
+        ev_host = evals.cpu().numpy()
+        self.last_stats = {"evals": int(ev_host.sum())}
+        if timing:
+            for (k, _, _), n in zip(descs, ev_host):
+                self.launch_evals.append((k, int(n)))
+        return {"best_loss": best_loss.cpu().numpy(), "best_k": best_k.cpu().numpy(), "best_P": best_P.cpu().numpy(),
+                "best_x": best_x, "per_k": [], "best_loss_dev": best_loss, "best_k_dev": best_k}
 
     def approximate_targets(self, targets, k_range: Optional[Sequence[int]] = None, opts=None,
                             reuse_host_buffers: bool = True) -> dict:

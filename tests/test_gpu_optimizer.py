@@ -323,3 +323,30 @@ def test_hamiltonian_template_finds_b_gate_parameters():
     U = basis.eval(d.Xk)
     assert np.abs(U - O.conversion_gain(d.Xk[0], d.Xk[1], d.Xk[2], d.Xk[3], d.Xk[4])).max() < 1e-12
     assert abs(O.cost(U, target, "makhlin_euclidean") - d.loss_result) < 3e-8 and d.loss_result < 2e-3 and d.cycles == 1
+
+
+def test_chained_sweep_matches_the_sequential_k_loop():
+    """The two-stream chained sweep (solved_in / solved_out flags, no host round trip between template sizes) must keep what
+    the sequential k-loop of optimizer.py:233-303 keeps: per target the smallest size that reaches the threshold.  Restart
+    outcomes are deterministic functions of (seed, target, restart) -- only the early-exit timing differs -- so the sizes
+    must agree target by target and every reported Xk must reproduce its loss in the oracle."""
+    from slam_decomposition_b200.utils.gates.custom_gates import RiSwapGate
+    rng = np.random.default_rng(21)
+    Nt = 3000
+    V = np.stack([O.haar_unitary(rng) for _ in range(Nt - 3)] + [O.CNOT, O.riswap(0.5), np.eye(4)]).astype(np.complex128)
+    out = {}
+    for mode in (True, False):
+        basis = CircuitTemplate(base_gates=[RiSwapGate(1 / 2)], maximum_span_guess=4, preseed=False)
+        opt = TemplateOptimizer(basis=basis, objective=BasicCost(), override_fail=True, training_restarts=6)
+        opt.pipeline = mode
+        np.random.seed(99)
+        out[mode] = opt.approximate_targets(V, range(1, 5), reuse_host_buffers=False)
+    a, b = out[True], out[False]
+    assert (a["success"] == 1).mean() > 0.999 and (b["success"] == 1).mean() > 0.999
+    both = (a["success"] == 1) & (b["success"] == 1)
+    assert (a["cycles"][both] == b["cycles"][both]).all()
+    assert a["cycles"][-3] == 2 and a["cycles"][-2] == 1 and a["cycles"][-1] in (1, 2)  # CNOT, sqrt(iSWAP), identity
+    for i in list(range(0, Nt, 211)) + [Nt - 3, Nt - 2, Nt - 1]:
+        k = int(a["cycles"][i])
+        tmpl = O.OracleTemplate("riswap", (0.5,), k=k)
+        assert abs(O.cost(tmpl.eval(a["Xk"][i, : tmpl.n_params]), V[i], "basic") - a["loss"][i]) < 1e-10
