@@ -21,13 +21,15 @@ def timed(fn, reps=3):
     return a.elapsed_time(b) / reps
 best = {}
 for rnd in range(3):  # interleaved rounds, best-of: clock ramp and order effects cancel
-    for mb in ("2", "3", "4"):
-        os.environ["SLAM_B200_COV_MINB"] = mb
-        for name, basis in cases:
-            ms = timed(lambda: pdv.coverage_histogram(basis, n, seed=2, hist=hist))
-            best[(mb, name)] = min(ms, best.get((mb, name), 1e9))
-for (mb, name), ms in sorted(best.items(), key=lambda kv: (kv[0][1], kv[0][0])):
-    print(f"{name} COV_MINB={mb}: {n / ms / 1e3:8.1f} Msamples/s", flush=True)
+    for sync in ("0", "1"):
+        os.environ["SLAM_B200_COV_SYNC"] = sync
+        for mb in ("2", "3", "4"):
+            os.environ["SLAM_B200_COV_MINB"] = mb
+            for name, basis in cases:
+                ms = timed(lambda: pdv.coverage_histogram(basis, n, seed=2, hist=hist))
+                best[(name, sync, mb)] = min(ms, best.get((name, sync, mb), 1e9))
+for (name, sync, mb), ms in sorted(best.items()):
+    print(f"{name} SYNC={sync} MINB={mb}: {n / ms / 1e3:8.1f} Msamples/s", flush=True)
 U = torch.as_tensor(bench.haar_targets(1 << 21, 99), device=dev)
 for mb in ("4", "3"):
     os.environ["SLAM_B200_WEYL_MINB"] = mb

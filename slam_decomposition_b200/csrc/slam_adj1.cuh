@@ -88,6 +88,9 @@ struct SmushGrad {
 // Backward through one slice.  In: R[c] = column c of the right product INCLUDING the slice, W[c] = row c of the left
 // environment EXCLUDING it.  Out: R[c] without the slice, W[c] including it; *d_gx, *d_gy = d loss / d amplitudes of this
 // slice; gate-level derivatives accumulated into `acc`.
+// SYNC: CTA-wide barriers between the sub-phases (eigen-decomposition | into the eigenbasis | divided differences and G |
+// parameter derivatives and back-transform), each 5-15 KB of code: see slam_fwd1.cuh (fwd1_gate) for why.
+template <bool SYNC = false>
 __device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, double gy, double dt, cd R[4][4], cd W[4][4],
                                                 double* d_gx, double* d_gy, SmushGrad& acc) {
   HermG A;
@@ -102,7 +105,9 @@ __device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, d
   A.u[4] = A.u[1];                               // (1,3)
   A.u[5] = A.u[0];                               // (2,3)
   cd Q[4][4];
+  if (SYNC) __syncthreads();
   herm_eig4(A, Q);
+  if (SYNC) __syncthreads();
   cd hp[4], ph[4];  // e^{-i dt lam / 2}, e^{-i dt lam}
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -135,6 +140,7 @@ __device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, d
       W[c][a] = tw[a];
     }
   }
+  if (SYNC) __syncthreads();
   // N = Phi o M,  M_ab = sum_c W[c][a] R[c][b]
   cd N[4][4];
   double ddt = 0.0;
@@ -188,6 +194,7 @@ __device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, d
         Gm[i][j] = g;
       }
   }
+  if (SYNC) __syncthreads();
   // d loss / d(Re H_ij) = dt Im(G_ij + G_ji),  d loss / d(Im H_ij) = dt Re(G_ij - G_ji),  d loss / d(H_ii) = dt Im G_ii
   // entries: (0,1),(2,3) = gy e^{-i pb};  (0,2),(1,3) = gx e^{-i pa};  (0,3) = gg e^{-i pg};  (1,2) = gc e^{-i pc}
   {
@@ -243,11 +250,11 @@ __device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, d
 }
 
 // loss only (forward evaluation + trace functional), one thread
-template <class PS>
+template <class PS, bool SYNC = false>
 __device__ __forceinline__ double fwd1_loss(const KTemplate& kt, const PS& ps, const double* __restrict__ V, int cost_kind,
                                             cd* T_out) {
   cd R[4][4];
-  fwd1_chain(kt, ps, R);
+  fwd1_chain<PS, GM_SMUSH, SYNC>(kt, ps, R);  // (only launched for parameter-bound smush templates)
   cd T = mkc(0.0, 0.0);
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -264,10 +271,10 @@ __device__ __forceinline__ double fwd1_loss(const KTemplate& kt, const PS& ps, c
 }
 
 // gradient sinks
-struct RowGrad {  // row of a [B, ldg] array
+struct RowGrad {  // row of a [B, ldg] array (row == nullptr: discard -- padding lanes of a phase-locked CTA)
   double* row;
   __device__ __forceinline__ void set(int j, double v) const {
-    if (j >= 0) row[j] = v;
+    if (j >= 0 && row) row[j] = v;
   }
 };
 struct StridedGrad {  // workspace vector interleaved across threads
@@ -285,11 +292,11 @@ struct StridedGrad {  // workspace vector interleaved across threads
 //                    so each entry is set once)
 // returns the loss; *T_out = Tr(V^dagger U) if non-null
 // ------------------------------------------------------------------------------------------------
-template <class PS, class GS>
+template <class PS, class GS, bool SYNC = false>
 __device__ __forceinline__ double adj1_loss_grad(const KTemplate& kt, const PS& ps, const double* __restrict__ V,
                                                  int cost_kind, GS& gs, cd* T_out) {
   cd R[4][4];  // [col][row]
-  fwd1_chain(kt, ps, R);
+  fwd1_chain<PS, GM_SMUSH, SYNC>(kt, ps, R);
   cd T = mkc(0.0, 0.0);
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -316,6 +323,7 @@ __device__ __forceinline__ double adj1_loss_grad(const KTemplate& kt, const PS& 
   const bool ph1q = kt.gate_kind == SLAM_GATE_SMUSH_1QPHASE;
   const int o = ph1q ? 8 : 4;  // first gx slot
   for (int i = kt.k; i >= 0; --i) {
+    if (SYNC) __syncthreads();
     if (!(kt.p1q[i][0] < 0 && kt.p1q[i][3] < 0)) {
       if (kt.vz_only) {
         // RZ = diag(e^{-i l/2}, e^{+i l/2}) on each qubit: d loss/dl = (1/2) (Im sum_lo - Im sum_hi) w r at the cut after the layer
@@ -342,7 +350,7 @@ __device__ __forceinline__ double adj1_loss_grad(const KTemplate& kt, const PS& 
         gs.set(kt.p1q[i][3], 0.5 * d3);
       } else {
         double2 t[6];
-#pragma unroll
+#pragma unroll 1
         for (int q = 0; q < 6; ++q) {
           const double v = ps.get(kt.p1q[i][q]);
           double s, c;
@@ -386,7 +394,7 @@ __device__ __forceinline__ double adj1_loss_grad(const KTemplate& kt, const PS& 
       SmushGrad acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       for (int it = Tn - 1; it >= 0; --it) {
         double dgx, dgy;
-        smush_slice_bwd(G, slot_val(kt, ps, g, o + it), slot_val(kt, ps, g, o + Tn + it), dt, R, W, &dgx, &dgy, acc);
+        smush_slice_bwd<SYNC>(G, slot_val(kt, ps, g, o + it), slot_val(kt, ps, g, o + Tn + it), dt, R, W, &dgx, &dgy, acc);
         int p;
         if ((p = kt.slot_param[g][o + it]) >= 0) gs.set(p, dgx);
         if ((p = kt.slot_param[g][o + Tn + it]) >= 0) gs.set(p, dgy);

@@ -17,33 +17,42 @@
 namespace slam {
 
 // The sample's P parameters are generated once, two per Philox block, into the thread's column of a shared-memory
-// table (entry j of thread t at xs[j * 128 + t]: conflict-free) and read from there by the chain.  Calling the generator
+// table (entry j of thread t at xs[j * CTA + t]: conflict-free) and read from there by the chain.  Calling the generator
 // per parameter access ran every Philox block twice; at P = 12 that was a third of the kernel's instructions.
+template <int CTA>
 struct StagedParams {
   const double* col;
-  __device__ __forceinline__ double get(int j) const { return col[j * 128]; }
+  __device__ __forceinline__ double get(int j) const { return col[j * CTA]; }
 };
 
-// GMT: gate mode fixed at compile time (-1 = runtime dispatch); MINB: resident CTAs per SM the register allocation targets
-template <int GMT, int MINB>
-__global__ void __launch_bounds__(128, MINB) coverage_kernel(uint64_t seed, int64_t first, int64_t n, double lo, double span,
-                                                             int nbins, unsigned long long* __restrict__ hist,
-                                                             double* __restrict__ coords, const __grid_constant__ KTemplate kt) {
+// GMT:  gate mode fixed at compile time (-1 = runtime dispatch)
+// MINB: 128-thread units per SM the register allocation targets (2: 255 registers, 3: 168, 4: 128)
+// SYNC: phase-locked variant -- ONE CTA of 128 * MINB threads per SM with barriers at the phase boundaries (slam_fwd1.cuh)
+template <int GMT, int MINB, bool SYNC>
+__global__ void __launch_bounds__(SYNC ? 128 * MINB : 128, SYNC ? 1 : MINB)
+coverage_kernel(uint64_t seed, int64_t first, int64_t n, double lo, double span, int nbins,
+                unsigned long long* __restrict__ hist, double* __restrict__ coords, const __grid_constant__ KTemplate kt) {
+  constexpr int CTA = SYNC ? 128 * MINB : 128;
   extern __shared__ double xs[];
   double* col = xs + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (int64_t)gridDim.x * CTA;
   const double scale = 2.0 * (double)nbins;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  // uniform trip count per CTA (the barriers of the SYNC variant sit inside the loop); out-of-range lanes recompute the
+  // last sample and drop the result
+  for (int64_t base = (int64_t)blockIdx.x * CTA; base < n; base += stride) {
+    const int64_t i = min(base + (int64_t)threadIdx.x, n - 1);
+    const bool valid = base + (int64_t)threadIdx.x < n;
     for (int jj = 0; 2 * jj < kt.P; ++jj) {
       double u0, u1;
       philox_u53_pair(seed, (uint64_t)(first + i), jj, &u0, &u1);
       // lo + span * u with a separate multiply and add (numpy does not fuse; keeps the stream bit-identical)
-      col[(2 * jj) * 128] = __dadd_rn(lo, __dmul_rn(span, u0));
-      if (2 * jj + 1 < kt.P) col[(2 * jj + 1) * 128] = __dadd_rn(lo, __dmul_rn(span, u1));
+      col[(2 * jj) * CTA] = __dadd_rn(lo, __dmul_rn(span, u0));
+      if (2 * jj + 1 < kt.P) col[(2 * jj + 1) * CTA] = __dadd_rn(lo, __dmul_rn(span, u1));
     }
-    StagedParams ps{col};
+    StagedParams<CTA> ps{col};
     cd R[4][4];
-    fwd1_chain<StagedParams, GMT>(kt, ps, R);
+    fwd1_chain<StagedParams<CTA>, GMT, SYNC>(kt, ps, R);
+    if (SYNC) __syncthreads();
     cd M[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
@@ -51,29 +60,32 @@ __global__ void __launch_bounds__(128, MINB) coverage_kernel(uint64_t seed, int6
       for (int r = 0; r < 4; ++r) M[r][c] = R[c][r];
     double c3[3];
     weyl_makhlin(M, SLAM_WEYL_FOLD, c3, nullptr);
-    if (coords) {
+    if (valid && coords) {
       coords[3 * i] = c3[0];
       coords[3 * i + 1] = c3[1];
       coords[3 * i + 2] = c3[2];
     }
-    if (hist) {
+    if (valid && hist) {
       int b0 = min(max((int)floor(c3[0] * scale), 0), nbins - 1);
       int b1 = min(max((int)floor(c3[1] * scale), 0), nbins - 1);
       int b2 = min(max((int)floor(c3[2] * scale), 0), nbins - 1);
       atomicAdd(hist + ((size_t)b0 * nbins + b1) * nbins + b2, 1ULL);
     }
+    if (SYNC) __syncthreads();
   }
 }
 
-template <int GMT, int MINB>
+template <int GMT, int MINB, bool SYNC>
 static int launch_coverage(const KTemplate& kt, uint64_t seed, int64_t first, int64_t n, double lo, double span, int nbins,
                            unsigned long long* hist, double* coords, int sms, cudaStream_t st) {
-  const int64_t want = (n + 127) / 128;
-  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 8 * MINB);  // grid-stride, a multiple of the SM count
-  const size_t smem = (size_t)std::max(kt.P, 1) * 128 * sizeof(double);
-  auto kern = coverage_kernel<GMT, MINB>;
+  constexpr int CTA = SYNC ? 128 * MINB : 128;
+  const int64_t want = (n + CTA - 1) / CTA;
+  // grid-stride, a multiple of the SM count
+  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * (SYNC ? 8 : 8 * MINB));
+  const size_t smem = (size_t)std::max(kt.P, 1) * CTA * sizeof(double);
+  auto kern = coverage_kernel<GMT, MINB, SYNC>;
   if (smem > 48 * 1024) SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, 128, smem, st>>>(seed, first, n, lo, span, nbins, hist, coords, kt);
+  kern<<<grid, CTA, smem, st>>>(seed, first, n, lo, span, nbins, hist, coords, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }
@@ -99,12 +111,20 @@ extern "C" int slam_coverage_mc(const SlamTemplateDesc* desc, uint64_t seed, int
   SLAM_CUDA_CHECK(cudaGetDevice(&dev));
   SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const double span = hi - lo;
-  // Resident CTAs per SM the kernels are compiled for (register cap 255 / 168 / 128).  Measured on B200, Msamples/s at
-  // 2 / 3 / 4 CTAs: sqrt(iSWAP) k=3 plain 1610 / 1936 / 2134, CNOT k=3 plain 1499 / 1852 / 2066, sqrt(iSWAP) k=3 smush
-  // 324 / 332 / 347 (scripts/cov_ab.py): the chains are latency bound, so 16 warps/SM win despite 160-1000 B of spills.
+  // 128-thread units per SM the kernels are compiled for (register cap 255 / 168 / 128).  Measured on B200, Msamples/s at
+  // 2 / 3 / 4 units: sqrt(iSWAP) k=3 plain 2355 / 2771 / 2928, CNOT k=3 plain 2338 / 2745 / 2903 (latency bound: 16 warps/SM
+  // win despite 160 B of spills); sqrt(iSWAP) k=3 smush, phase-locked, 542 / 542 / 515 (scripts/cov_ab.py).
   const char* e = getenv("SLAM_B200_COV_MINB");
   const int minb = e ? atoi(e) : 0;
-#define SLAM_COV(GM, MB) return launch_coverage<GM, MB>(kt, seed, first_sample, n_samples, lo, span, nbins, hist, coords, sms, st)
+  // Phase-locked variant (one CTA per SM, barriers at the layer / gate / slice boundaries): on for the smush templates,
+  // whose kernel is 75 KB of code (sqrt(iSWAP) k=3 smush 458 -> 542, CNOT k=2 smush 424 -> 454 Msamples/s); off for the
+  // closed-form gates, whose hot code fits the 32 KB instruction cache (2928 vs 2862 Msamples/s).
+  const char* es = getenv("SLAM_B200_COV_SYNC");
+  const bool sync = es ? atoi(es) != 0 : kt.gmode == GM_SMUSH;
+#define SLAM_COV(GM, MB)                                                                                                  \
+  return (sync && (size_t)kt.P * 128 * MB * sizeof(double) <= 200 * 1024)                                                  \
+             ? launch_coverage<GM, MB, true>(kt, seed, first_sample, n_samples, lo, span, nbins, hist, coords, sms, st)   \
+             : launch_coverage<GM, MB, false>(kt, seed, first_sample, n_samples, lo, span, nbins, hist, coords, sms, st)
   switch (kt.gmode) {
     case GM_SYM:
       if (minb == 2) SLAM_COV(GM_SYM, 2);
@@ -119,9 +139,9 @@ extern "C" int slam_coverage_mc(const SlamTemplateDesc* desc, uint64_t seed, int
       if (minb == 3) SLAM_COV(GM_DENSE, 3);
       SLAM_COV(GM_DENSE, 4);
     default:
-      if (minb == 2) SLAM_COV(GM_SMUSH, 2);
       if (minb == 3) SLAM_COV(GM_SMUSH, 3);
-      SLAM_COV(GM_SMUSH, 4);
+      if (minb == 4) SLAM_COV(GM_SMUSH, 4);
+      SLAM_COV(GM_SMUSH, 2);
   }
 #undef SLAM_COV
   return SLAM_OK;

@@ -47,17 +47,13 @@ struct FdArgs {
   int64_t T;
 };
 
-// parameters of a workspace vector with one entry shifted: x + h e_j
-struct ShiftedParams {
-  const double* p;
-  int64_t stride;
-  int j;
-  double h;
-  __device__ __forceinline__ double get(int i) const {
-    const double v = p[(int64_t)i * stride];
-    return i == j ? v + h : v;
-  }
-};
+// out-of-line copy of the adjoint pass (called from the initial point and from every accepted step)
+static __device__ __noinline__ void adj1_nl(const KTemplate* kt, const double* p, int64_t stride, const double* V,
+                                            int cost_kind, double* g, int64_t gstride) {
+  StridedParams ps{p, stride};
+  StridedGrad gsw{g, gstride};
+  adj1_loss_grad(*kt, ps, V, cost_kind, gsw, nullptr);
+}
 
 // MODE 0: forward differences (scipy's jac=None), 1: central differences, 2: analytic adjoint gradient through the
 // smush slices (slam_adj1.cuh; GM_SMUSH templates only) -- one backward pass instead of P + 1 forward evaluations
@@ -93,18 +89,15 @@ __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ F
     target_info_init(ti, A.V + t * 32, A.cost_kind);
 
     auto f_at = [&](int v) -> double {
-      StridedParams ps{&vec(v, 0), T};
       ++evals;
-      return objective_value(kt, ps, ti, A.cost_kind);
+      return objective_value_nl(&kt, &vec(v, 0), T, -1, 0.0, &ti, A.cost_kind);
     };
     // gradient of buffer xb into buffer gb (fx = objective at xb); returns max |projected g|
     auto grad_at = [&](int xb, int gb, double fx) -> double {
       double gmax = 0.0;
       if (MODE == 2) {
-        StridedParams ps{&vec(xb, 0), T};
-        StridedGrad gsw{&vec(gb, 0), T};
         for (int j = 0; j < n; ++j) vec(gb, j) = 0.0;
-        adj1_loss_grad(kt, ps, A.V + t * 32, A.cost_kind, gsw, nullptr);
+        adj1_nl(&kt, &vec(xb, 0), T, A.V + t * 32, A.cost_kind, &vec(gb, 0), T);
         ++evals;
       }
       for (int j = 0; j < n; ++j) {
@@ -112,12 +105,11 @@ __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ F
         if (MODE == 2) {
           gj = vec(gb, j);
         } else if (MODE == 1) {
-          ShiftedParams pp{&vec(xb, 0), T, j, h_cen}, pm{&vec(xb, 0), T, j, -h_cen};
-          gj = (objective_value(kt, pp, ti, A.cost_kind) - objective_value(kt, pm, ti, A.cost_kind)) / (2.0 * h_cen);
+          gj = (objective_value_nl(&kt, &vec(xb, 0), T, j, h_cen, &ti, A.cost_kind) -
+                objective_value_nl(&kt, &vec(xb, 0), T, j, -h_cen, &ti, A.cost_kind)) / (2.0 * h_cen);
           evals += 2;
         } else {
-          ShiftedParams pp{&vec(xb, 0), T, j, h_fwd};
-          gj = (objective_value(kt, pp, ti, A.cost_kind) - fx) / h_fwd;
+          gj = (objective_value_nl(&kt, &vec(xb, 0), T, j, h_fwd, &ti, A.cost_kind) - fx) / h_fwd;
           ++evals;
         }
         if (MODE != 2) vec(gb, j) = gj;

@@ -257,7 +257,7 @@ __device__ __forceinline__ void fwd1_layer(const KTemplate& kt, const PS& ps, in
     build_rz(make_double2(c, s), A);
   } else {
     double2 t[6];
-#pragma unroll
+#pragma unroll 1  // one copy of the (cos, sin) routine: the forward-only kernels are instruction-fetch bound
     for (int q = 0; q < 6; ++q) {
       const double v = ps.get(kt.p1q[i][q]);
       fast_sincos((q == 0 || q == 3) ? 0.5 * v : v, &s, &c);
@@ -274,7 +274,10 @@ __device__ __forceinline__ void fwd1_layer(const KTemplate& kt, const PS& ps, in
 }
 
 // GMT >= 0 fixes the gate mode at compile time (the other modes' code is not generated); -1 = runtime dispatch on kt.gmode
-template <class PS, int GMT = -1>
+// SYNC: CTA-wide barriers at the phase boundaries (every layer / gate / slice).  All threads of a forward-only kernel run
+// the same control flow, so the barriers cost nothing but keep the CTA's warps inside the SAME few KB of code at any time;
+// without them the warps spread over the whole kernel (50-80 KB) and thrash the 32 KB L1.5 instruction cache.
+template <class PS, int GMT = -1, bool SYNC = false>
 __device__ __forceinline__ void fwd1_gate(const KTemplate& kt, const PS& ps, int g, cd R[4][4]) {
   const int gmode = (GMT >= 0) ? GMT : kt.gmode;
   if (gmode == GM_SYM) {
@@ -318,6 +321,7 @@ __device__ __forceinline__ void fwd1_gate(const KTemplate& kt, const PS& ps, int
                      slot_val(kt, ps, g, 3), 0.0, 0.0);
     const double dt = slot_val(kt, ps, g, o + 2 * T) / (double)T;  // timestep = t / N (hamiltonian.py:136-137)
     for (int it = 0; it < T; ++it) {
+      if (SYNC) __syncthreads();
       cd Y[4][4];
       smush_slice(G, slot_val(kt, ps, g, o + it), slot_val(kt, ps, g, o + T + it), dt, Y);
       left_mul(Y, R);  // later slices multiply on the left (hamiltonian.py:143)
@@ -325,15 +329,17 @@ __device__ __forceinline__ void fwd1_gate(const KTemplate& kt, const PS& ps, int
   }
 }
 
-template <class PS, int GMT = -1>
+template <class PS, int GMT = -1, bool SYNC = false>
 __device__ __forceinline__ void fwd1_chain(const KTemplate& kt, const PS& ps, cd R[4][4]) {
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int r = 0; r < 4; ++r) R[c][r] = mkc(c == r ? 1.0 : 0.0, 0.0);
   for (int i = 0; i <= kt.k; ++i) {
+    if (SYNC) __syncthreads();
     fwd1_layer(kt, ps, i, R);
-    if (i < kt.k) fwd1_gate<PS, GMT>(kt, ps, i, R);
+    if (SYNC) __syncthreads();
+    if (i < kt.k) fwd1_gate<PS, GMT, SYNC>(kt, ps, i, R);
   }
 }
 

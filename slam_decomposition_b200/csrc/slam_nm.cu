@@ -67,9 +67,8 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs 
     TargetInfo ti;
     target_info_init(ti, A.V + t * 32, A.cost_kind);
     auto f_at = [&](int v) -> double {
-      StridedParams ps{&vec(v, 0), T};
       ++evals;
-      return objective_value(kt, ps, ti, A.cost_kind);
+      return objective_value_nl(&kt, &vec(v, 0), T, -1, 0.0, &ti, A.cost_kind);
     };
     // initial simplex (scipy: y[k] *= 1.05, or 0.00025 if zero)
     for (int j = 0; j < n; ++j) {

@@ -91,4 +91,25 @@ __device__ __forceinline__ double objective_value(const KTemplate& kt, const PS&
   return 1.0 - c * F;
 }
 
+// parameters of a workspace vector, optionally with one entry shifted: x + h e_j (j < 0: no shift)
+struct ShiftedParams {
+  const double* p;
+  int64_t stride;
+  int j;
+  double h;
+  __device__ __forceinline__ double get(int i) const {
+    const double v = p[(int64_t)i * stride];
+    return i == j ? v + h : v;
+  }
+};
+
+// ONE out-of-line copy of the objective per kernel.  The thread-per-problem optimisers evaluate it from several places
+// (line search, every finite difference, every simplex move); inlined at each of them the kernels were 320-720 KB of
+// code against a 32 KB instruction cache.  `kt` points at the kernel's __grid_constant__ parameter.
+static __device__ __noinline__ double objective_value_nl(const KTemplate* kt, const double* p, int64_t stride, int j,
+                                                         double h, const TargetInfo* ti, int cost_kind) {
+  ShiftedParams ps{p, stride, j, h};
+  return objective_value(*kt, ps, *ti, cost_kind);
+}
+
 }  // namespace slam

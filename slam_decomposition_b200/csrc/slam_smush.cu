@@ -7,13 +7,23 @@
 namespace slam {
 
 // ---- K1 for parameter-bound smush templates: one thread per parameter row ---------------------------
-__global__ void __launch_bounds__(128) smush_eval_kernel(const double* __restrict__ x, int64_t ldx, double* __restrict__ U,
-                                                         int64_t B, const __grid_constant__ KTemplate kt) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+// 128-thread CTAs, two per SM (the kernels need ~250 registers).  The phase-locked form that pays off in the coverage kernel
+// (CTA-wide barriers at the layer / gate / slice boundaries, slam_fwd1.cuh) was measured SLOWER here -- 597 vs 661 M evals/s
+// (K1), 170 vs 176 M loss+grad/s (K2) at sqrt(iSWAP) k=3: these kernels read their parameter rows from global memory, and a
+// barrier makes every warp wait for the slowest row -- so SYNC stays off; padding lanes still recompute the last row so that
+// the flag can be flipped for experiments.
+constexpr int kSmushCta = 128;
+constexpr bool kSmushSync = false;
+
+__global__ void __launch_bounds__(kSmushCta) smush_eval_kernel(const double* __restrict__ x, int64_t ldx,
+                                                                  double* __restrict__ U, int64_t B,
+                                                                  const __grid_constant__ KTemplate kt) {
+  const int64_t b0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t b = min(b0, B - 1);
   GlobalParams ps{x + b * ldx};
   cd R[4][4];
-  fwd1_chain(kt, ps, R);
+  fwd1_chain<GlobalParams, GM_SMUSH, kSmushSync>(kt, ps, R);
+  if (b0 >= B) return;
   double* out = U + b * 32;
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -22,8 +32,8 @@ __global__ void __launch_bounds__(128) smush_eval_kernel(const double* __restric
 }
 
 int smush_eval_launch(const KTemplate& kt, const double* x, int64_t ldx, double* U, int64_t B, cudaStream_t st) {
-  const unsigned grid = (unsigned)((B + 127) / 128);
-  smush_eval_kernel<<<grid, 128, 0, st>>>(x, ldx, U, B, kt);
+  const unsigned grid = (unsigned)((B + kSmushCta - 1) / kSmushCta);
+  smush_eval_kernel<<<grid, kSmushCta, 0, st>>>(x, ldx, U, B, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }
@@ -32,24 +42,27 @@ int smush_eval_launch(const KTemplate& kt, const double* x, int64_t ldx, double*
 // (replaces objective_func + scipy's (P+1)-evaluation finite-difference gradient for these templates,
 //  optimizer.py:191-214, 270-278)
 template <bool WANT_GRAD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kSmushCta)
 smush_loss_grad_kernel(const double* __restrict__ x, int64_t ldx, const double* __restrict__ V, int64_t Nt,
                        const int32_t* __restrict__ tgt_idx, int cost_kind, double* __restrict__ loss,
                        double* __restrict__ grad, int64_t ldg, double* __restrict__ trace, int64_t B,
                        const __grid_constant__ KTemplate kt) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  const int64_t b0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = b0 < B;
+  const int64_t b = min(b0, B - 1);
   const int64_t tgt = tgt_idx ? (int64_t)tgt_idx[b] : (b % Nt);
   GlobalParams ps{x + b * ldx};
   cd T;
   double l;
   if (WANT_GRAD) {
-    RowGrad gs{grad + b * ldg};
-    for (int j = 0; j < kt.P; ++j) gs.row[j] = 0.0;  // parameters bound to no slot keep a zero derivative
-    l = adj1_loss_grad(kt, ps, V + tgt * 32, cost_kind, gs, &T);
+    RowGrad gs{valid ? grad + b * ldg : nullptr};
+    if (valid)
+      for (int j = 0; j < kt.P; ++j) gs.row[j] = 0.0;  // parameters bound to no slot keep a zero derivative
+    l = adj1_loss_grad<GlobalParams, RowGrad, kSmushSync>(kt, ps, V + tgt * 32, cost_kind, gs, &T);
   } else {
-    l = fwd1_loss(kt, ps, V + tgt * 32, cost_kind, &T);
+    l = fwd1_loss<GlobalParams, kSmushSync>(kt, ps, V + tgt * 32, cost_kind, &T);
   }
+  if (!valid) return;
   loss[b] = l;
   if (trace) {
     trace[2 * b] = T.re;
@@ -60,11 +73,11 @@ smush_loss_grad_kernel(const double* __restrict__ x, int64_t ldx, const double* 
 int smush_loss_grad_launch(const KTemplate& kt, const double* x, int64_t ldx, const double* V, int64_t Nt,
                            const int32_t* tgt_idx, int cost_kind, double* loss, double* grad, int64_t ldg, double* trace,
                            int64_t B, cudaStream_t st) {
-  const unsigned grid = (unsigned)((B + 127) / 128);
+  const unsigned grid = (unsigned)((B + kSmushCta - 1) / kSmushCta);
   if (grad)
-    smush_loss_grad_kernel<true><<<grid, 128, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, kt);
+    smush_loss_grad_kernel<true><<<grid, kSmushCta, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, kt);
   else
-    smush_loss_grad_kernel<false><<<grid, 128, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, nullptr, 0, trace, B, kt);
+    smush_loss_grad_kernel<false><<<grid, kSmushCta, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, nullptr, 0, trace, B, kt);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }

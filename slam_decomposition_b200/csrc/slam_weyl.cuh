@@ -148,7 +148,9 @@ __device__ __forceinline__ void weyl_makhlin(const cd U[4][4], int flags, double
   }
   if (!c_out) return;
 
-  // joint Jacobi sweeps on (Re m, Im m)
+  // joint Jacobi sweeps on (Re m, Im m).  Not unrolled: the kernels that inline this function are instruction-fetch bound
+  // (ncu: stall_no_instruction 3-5 per issue in the coverage kernels with the 12 sweeps unrolled, 46 KB of code for K3 alone)
+#pragma unroll 1
   for (int sweep = 0; sweep < 12; ++sweep) {
     double off = 0.0;
 #pragma unroll
@@ -167,13 +169,20 @@ __device__ __forceinline__ void weyl_makhlin(const cd U[4][4], int flags, double
     joint_rotation<1, 3>(a, b);
     joint_rotation<2, 3>(a, b);
   }
-  // two_S = angle(ev / sqrt(det)) / pi, principal square root
-  const double half_det_phase = 0.5 * atan2(det.im, det.re);
+  // two_S = angle(ev / sqrt(det)) / pi, principal square root.  The five atan2 run through ONE copy of the routine (a rolled
+  // loop over a small local array): inlined five times they were 660 of the function's 2950 instructions, and the kernels
+  // that use it are instruction-fetch bound (hot code above the 32 KB L1.5 instruction cache).
+  double ang_y[5] = {det.im, b[sym_idx(0, 0)], b[sym_idx(1, 1)], b[sym_idx(2, 2)], b[sym_idx(3, 3)]};
+  double ang_x[5] = {det.re, a[sym_idx(0, 0)], a[sym_idx(1, 1)], a[sym_idx(2, 2)], a[sym_idx(3, 3)]};
+  double ang[5];
+#pragma unroll 1
+  for (int j = 0; j < 5; ++j) ang[j] = atan2(ang_y[j], ang_x[j]);
+  const double half_det_phase = 0.5 * ang[0];
   const double inv_pi = 0.31830988618379067154, pi = 3.14159265358979323846;
   double S[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    double th = atan2(b[sym_idx(j, j)], a[sym_idx(j, j)]) - half_det_phase;
+    double th = ang[j + 1] - half_det_phase;
     if (th > pi) th -= 2.0 * pi;
     if (th <= -pi) th += 2.0 * pi;
     double two_s = th * inv_pi;
