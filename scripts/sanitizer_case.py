@@ -25,5 +25,22 @@ b = pdv.smush_template(*BASES["sqiSwap"], 2)
 pdv.coverage_histogram(b, 2000, seed=3, nbins=16)
 engine.pd_trajectory(torch.zeros((3, 8), device="cuda", dtype=torch.float64), torch.ones((3, 4), device="cuda", dtype=torch.float64),
                      torch.ones((3, 4), device="cuda", dtype=torch.float64), 0.1)
+# round-1 additions: plain coverage (staged Philox), smush K1/K2 (adjoint), K5c in all gradient modes, chained sweep
+pdv.coverage_histogram(pdv.plain_template(*BASES["CNOT"], 3), 3000, seed=4, nbins=16)
+X = torch.as_tensor(rng.uniform(-2, 2, (70, b.desc.n_params)), device="cuda")
+engine.template_eval(b.desc, X)
+engine.loss_grad(b.desc, X, V)
+engine.loss_grad(b.desc, X, V, want_grad=False)
+for mode in (0, 1, 2):
+    opts = engine.opt_defaults(); opts.max_iter = 6
+    engine.fd_lbfgs_solve(b.desc, V, 3, opts, seed=5, central=mode)
+from slam_decomposition_b200.basis import CircuitTemplate
+from slam_decomposition_b200.cost_function import BasicCost
+from slam_decomposition_b200.optimizer import TemplateOptimizer
+from slam_decomposition_b200.utils.gates.custom_gates import RiSwapGate
+opt = TemplateOptimizer(CircuitTemplate(base_gates=[RiSwapGate(0.5)], maximum_span_guess=3, preseed=False), BasicCost(),
+                        override_fail=True, training_restarts=2)
+o = engine.opt_defaults(); o.max_iter = 30
+opt.approximate_targets(V.cpu().numpy(), range(1, 4), opts=o)
 torch.cuda.synchronize()
 print("sanitizer case done")

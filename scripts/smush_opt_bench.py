@@ -40,3 +40,10 @@ for mode in ("adjoint", True):
 nm = engine.nm_defaults(); nm.cost_kind = _lib.COST_BASIC; nm.max_iter = 2500
 ms = timed(lambda: engine.nm_solve(basis.desc, Vt[:1024], 4, nm, x0=x0[:1024, :4].contiguous()), reps=1)
 print(f"K5b Nelder-Mead: {ms:8.1f} ms for 1024 targets x 4 restarts")
+# throughput at scale (several waves of problems per thread): random starts, the reference's U(-4pi, 4pi) box
+for NtL in (32768, 131072):
+    VL = Vt[torch.arange(NtL, device=dev) % Nt].contiguous()
+    opts = engine.opt_defaults(); opts.f_far = 1e-4; opts.x0_lo, opts.x0_hi = -4 * math.pi, 4 * math.pi
+    ev = torch.zeros(1, dtype=torch.int64, device=dev)
+    ms = timed(lambda: engine.fd_lbfgs_solve(basis.desc, VL, R, opts, seed=11, central="adjoint", evals=ev), reps=1)
+    print(f"K5c adjoint at scale: {NtL} targets x {R} restarts: {ms:8.1f} ms, {ev.item() / 2 / ms / 1e3:6.1f} M loss+grad/s")

@@ -55,6 +55,14 @@ static __device__ __noinline__ double adj1_nl(const KTemplate* kt, const double*
   return adj1_loss_grad(*kt, ps, V, cost_kind, gsw, nullptr);
 }
 
+// phase-locked copy for the tick kernel: every thread of the CTA calls it in the same tick (CTA-wide barriers inside)
+static __device__ __noinline__ double adj1_nl_sync(const KTemplate* kt, const double* p, int64_t stride, const double* V,
+                                                   int cost_kind, double* g, int64_t gstride) {
+  StridedParams ps{p, stride};
+  StridedGrad gsw{g, gstride};
+  return adj1_loss_grad<StridedParams, StridedGrad, true>(*kt, ps, V, cost_kind, gsw, nullptr);
+}
+
 // MODE 0: forward differences (scipy's jac=None), 1: central differences, 2: analytic adjoint gradient through the
 // smush slices (slam_adj1.cuh; GM_SMUSH templates only) -- one backward pass instead of P + 1 forward evaluations
 template <int MODE>
@@ -293,32 +301,45 @@ __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ F
 // ------------------------------------------------------------------------------------------------------------------
 enum { AST_IDLE = 0, AST_INIT = 1, AST_LS = 2 };
 
-__global__ void __launch_bounds__(128) adj_lbfgs_kernel(const __grid_constant__ FdArgs A, const __grid_constant__ KTemplate kt) {
+// Bookkeeping layout.  (x, g) double-buffered and the (s, y) history stay in the interleaved global workspace; the working
+// vector of the two-loop recursion / the search direction `dv` and two scratch vectors live in THREAD-LOCAL arrays.  That
+// is what makes the bookkeeping cheap: with everything behind one global pointer the compiler must keep every load after
+// the previous store (possible aliasing), which serialised ~1700 L2 round trips per tick and left the evaluations with 15 %
+// of the time.  Every loop below either only loads from global memory (pipelined, unrolled) or only stores to it, and the
+// axpy of one history pair is fused with the dot product of the next (m + 1 dependent passes per loop instead of 2 m).
+constexpr int kAdjCta = 256;  // one CTA per SM (the evaluation needs ~255 registers), phase-locked
+constexpr int kAdjHist = kFdHist;  // (s, y) pairs kept, in double.  Six float pairs were measured: +16 % evaluations/s (the
+                                   // history loads are what the bookkeeping waits for: 52 % of the stall samples, 109 MB of
+                                   // workspace against a 126 MB L2) but +21 % evaluations on the near-singular smush
+                                   // landscapes and fewer solved targets -- no net gain, so the history stays exact
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int NQ>
+__global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_constant__ FdArgs A, const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
-  const int m = kFdHist;
+  const int m = kAdjHist;
   const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t T = A.T;
   double* ws = A.ws + tidg;
-  auto vec = [&](int v, int j) -> double& { return ws[((int64_t)v * n + j) * T]; };
-  const int V_D = 4, V_S = 5, V_Y = 5 + m;
+  auto vecp = [&](int v) -> double* { return ws + (int64_t)v * n * T; };  // entry j at [j * T]
+  // history behind the four (x, g) vectors: pair slot i at hs(i) / hy(i), entry j at [j * T]
+  auto hs = [&](int slot) -> double* { return ws + (int64_t)(4 + slot) * n * T; };
+  auto hy = [&](int slot) -> double* { return ws + (int64_t)(4 + m + slot) * n * T; };
   const int64_t total = A.Nt * (int64_t)A.restarts;
-  constexpr unsigned FULL = 0xffffffffu;
-  auto proj = [&](int xb, int j, double gj) -> double {  // projected gradient component (box bounds)
-    if (A.lower) {
-      const double xj = vec(xb, j);
-      if ((xj <= A.lower[j] && gj > 0.0) || (xj >= A.upper[j] && gj < 0.0)) return 0.0;
-    }
-    return gj;
-  };
+  const bool bounded = A.lower != nullptr;
 
   int state = AST_IDLE, cur = 0, iter = 0, hcount = 0, hpos = 0, ls = 0;
   bool exhausted = false, slow = false;
   int64_t pid = 0, t = 0;
   double f = 0.0, alpha = 1.0, gde = 0.0, gamma = 1.0, f_chk = 0.0;
-  double rho[kFdHist], alp[kFdHist];
+  double rho[kAdjHist], alp[kAdjHist];
+  double dv[NQ], t1[NQ], t2[NQ];
   unsigned long long evals = 0;
-  for (int v = 0; v < 4; ++v)
-    for (int j = 0; j < n; ++j) vec(v, j) = 0.0;  // idle lanes evaluate their (finite) trial buffer
+  for (int v = 0; v < 4; ++v) {
+    double* p = vecp(v);
+    for (int j = 0; j < n; ++j) p[j * T] = 0.0;  // idle lanes evaluate their (finite) trial buffer
+  }
 
   while (true) {
     // ---------------- fetch -------------------------------------------------------------------------------
@@ -340,39 +361,60 @@ __global__ void __launch_bounds__(128) adj_lbfgs_kernel(const __grid_constant__ 
         continue;
       }
       cur = 0;  // trial buffer = vectors (2, 3)
+      double* x1 = vecp(2);
       for (int j = 0; j < n; ++j) {
         double x = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
-        if (A.lower) x = fmin(fmax(x, A.lower[j]), A.upper[j]);
-        vec(2, j) = x;
+        if (bounded) x = fmin(fmax(x, A.lower[j]), A.upper[j]);
+        x1[j * T] = x;
       }
       state = AST_INIT;
       iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false;
     }
-    __syncwarp();
-    if (__all_sync(FULL, state == AST_IDLE)) break;
+    // CTA-wide vote = the tick barrier: the CTA's warps enter the evaluation together and, with the barriers inside it,
+    // walk through its 200 KB of code in step (one instruction stream through the 32 KB instruction cache instead of eight)
+    if (__syncthreads_and(state == AST_IDLE)) break;
 
-    // ---------------- one loss + gradient evaluation per thread (warp-convergent) ---------------------------
-    const int XT = 2 * (cur ^ 1), GT = XT + 1;
-    for (int j = 0; j < n; ++j) vec(GT, j) = 0.0;
-    const double ft = adj1_nl(&kt, &vec(XT, 0), T, A.V + t * 32, A.cost_kind, &vec(GT, 0), T);
+    // ---------------- one loss + gradient evaluation per thread (CTA-convergent) ----------------------------
+    double* xt = vecp(2 * (cur ^ 1));
+    double* gt = xt + (int64_t)n * T;
+    for (int j = 0; j < n; ++j) gt[j * T] = 0.0;
+    const double ft = adj1_nl_sync(&kt, xt, T, A.V + t * 32, A.cost_kind, gt, T);
     if (state == AST_IDLE) continue;
     ++evals;
 
     // ---------------- bookkeeping ---------------------------------------------------------------------------
-    const int X = 2 * cur, G = X + 1;
+    const double* x = vecp(2 * cur);
+    const double* g = x + (int64_t)n * T;
     const bool first = state == AST_INIT;
     bool done = false;
     int reason = 0;
     if (first || ft <= f + kArmijoFd * gde) {
       // ---- accept ----
-      if (!first) {
-        double sy = 0.0, yy = 0.0;
-        for (int j = 0; j < n; ++j) {
-          const double sv = vec(XT, j) - vec(X, j), yv = vec(GT, j) - vec(G, j);
-          vec(V_S + hpos, j) = sv;
-          vec(V_Y + hpos, j) = yv;
+      // t1 <- projected gradient at the accepted point (also the start of the two-loop recursion); history pair
+      double gmax = 0.0, gg = 0.0, sy = 0.0, yy = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        const double xtj = xt[j * T], gtj = gt[j * T];
+        double gp = gtj;
+        if (bounded && ((xtj <= A.lower[j] && gtj > 0.0) || (xtj >= A.upper[j] && gtj < 0.0))) gp = 0.0;
+        t1[j] = gp;
+        gmax = fmax(gmax, fabs(gp));
+        gg = fma(gp, gp, gg);
+        if (!first) {
+          const double sv = xtj - x[j * T], yv = gtj - g[j * T];
+          dv[j] = sv;  // (the old direction is dead once the step is accepted)
+          t2[j] = yv;
           sy = fma(sv, yv, sy);
           yy = fma(yv, yv, yy);
+        }
+      }
+      if (!first) {
+        double* sn = hs(hpos);
+        double* yn = hy(hpos);
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+          sn[j * T] = dv[j];
+          yn[j * T] = t2[j];
         }
         if (sy > 1e-14 * yy && yy > 0.0) {  // cautious update
           rho[hpos] = 1.0 / sy;
@@ -386,15 +428,8 @@ __global__ void __launch_bounds__(128) adj_lbfgs_kernel(const __grid_constant__ 
       } else {
         f_chk = ft;
       }
-      cur ^= 1;  // the trial point becomes the current point: (X, G) = (XT, GT) from here on
+      cur ^= 1;  // the trial point becomes the current point
       f = ft;
-      double gmax = 0.0, gg = 0.0;
-      for (int j = 0; j < n; ++j) {
-        const double gp = proj(XT, j, vec(GT, j));
-        vec(V_D, j) = gp;
-        gmax = fmax(gmax, fabs(gp));
-        gg = fma(gp, gp, gg);
-      }
       if (!first && (iter & 31) == 0) {  // progress checkpoint (same rule as the sequential form)
         slow = f > 0.97 * f_chk;
         f_chk = f;
@@ -407,45 +442,85 @@ __global__ void __launch_bounds__(128) adj_lbfgs_kernel(const __grid_constant__ 
       else if (A.early_exit && (iter & 3) == 0 && *((volatile int32_t*)(A.solved + t)) != 0) reason = 6;
       done = reason != 0;
       if (!done) {
-        // two-loop recursion on the projected gradient (in V_D)
-        for (int hh = 0; hh < hcount; ++hh) {
+        // two-loop recursion, q = dv <- t1.  First loop, newest to oldest: a_i = rho_i s_i.q ; q -= a_i y_i -- the axpy of
+        // pair i is fused with the dot product of pair i+1.
+        for (int j = 0; j < n; ++j) dv[j] = t1[j];
+        double a_prev = 0.0;
+        const double* y_prev = hy(0);
+        for (int hh = 0; hh <= hcount; ++hh) {
           int slot = hpos - 1 - hh;
           if (slot < 0) slot += m;
-          double a = 0.0;
-          for (int j = 0; j < n; ++j) a = fma(vec(V_S + slot, j), vec(V_D, j), a);
-          a *= rho[slot];
-          alp[slot] = a;
-          for (int j = 0; j < n; ++j) vec(V_D, j) = fma(-a, vec(V_Y + slot, j), vec(V_D, j));
+          const bool last = hh == hcount;  // last pass: only the pending axpy
+          const double* sk = hs(last ? 0 : slot);
+          if (hh + 1 < hcount) {  // next pass's vectors on their way from DRAM / far L2 while this one computes
+            int nx = slot - 1;
+            if (nx < 0) nx += m;
+            const double* ps = hs(nx);
+            const double* py = hy(slot);
+            for (int j = 0; j < n; ++j) {
+              prefetch_l2(ps + j * T);
+              prefetch_l2(py + j * T);
+            }
+          }
+          double acc = 0.0;
+#pragma unroll 4
+          for (int j = 0; j < n; ++j) {
+            const double qj = hh == 0 ? dv[j] : fma(-a_prev, y_prev[j * T], dv[j]);  // (no load in the first pass: the
+                                                                                     // history may be uninitialised)
+            dv[j] = qj;
+            acc = fma(sk[j * T], qj, acc);
+          }
+          if (!last) {
+            a_prev = acc * rho[slot];
+            alp[slot] = a_prev;
+            y_prev = hy(slot);
+          }
         }
-        if (hcount > 0)
-          for (int j = 0; j < n; ++j) vec(V_D, j) *= gamma;
-        for (int hh = hcount - 1; hh >= 0; --hh) {
+        // second loop, oldest to newest: b_i = rho_i y_i.r ; r += (alp_i - b_i) s_i, with the initial scaling r = gamma q
+        // folded into the first pass
+        double c_prev = 0.0;
+        const double* s_prev = hs(0);
+        const double scale0 = hcount > 0 ? gamma : 1.0;
+        for (int hh = hcount - 1; hh >= -1; --hh) {
           int slot = hpos - 1 - hh;
           if (slot < 0) slot += m;
-          double b = 0.0;
-          for (int j = 0; j < n; ++j) b = fma(vec(V_Y + slot, j), vec(V_D, j), b);
-          const double c = alp[slot] - b * rho[slot];
-          for (int j = 0; j < n; ++j) vec(V_D, j) = fma(c, vec(V_S + slot, j), vec(V_D, j));
+          if (slot >= m) slot -= m;
+          const bool last = hh < 0;
+          const bool firstpass = hh == hcount - 1;
+          const double* yk = hy(last ? 0 : slot);
+          double acc = 0.0;
+#pragma unroll 4
+          for (int j = 0; j < n; ++j) {
+            const double rj = firstpass ? scale0 * dv[j] : fma(c_prev, s_prev[j * T], dv[j]);
+            dv[j] = rj;
+            acc = fma(yk[j * T], rj, acc);
+          }
+          if (!last) {
+            c_prev = alp[slot] - acc * rho[slot];
+            s_prev = hs(slot);
+          }
         }
+        // d = -r ; g.d
         double gd = 0.0;
         for (int j = 0; j < n; ++j) {
-          const double d = -vec(V_D, j);
-          vec(V_D, j) = d;
-          gd = fma(vec(GT, j), d, gd);
+          const double d = -dv[j];
+          dv[j] = d;
+          gd = fma(t1[j], d, gd);  // (projected gradient; equals g.d on the free variables)
         }
         alpha = 1.0;
         if (hcount == 0 || !(gd < 0.0)) {  // first step or not a descent direction: steepest descent, unit length
           hcount = 0;
-          for (int j = 0; j < n; ++j) vec(V_D, j) = -proj(XT, j, vec(GT, j));
+          for (int j = 0; j < n; ++j) dv[j] = -t1[j];
           alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
         }
         ls = 0;
         state = AST_LS;
       }
     } else {
-      // ---- reject: backtrack along the stored direction; cubic through (0, f, gde/alpha) and (alpha, ft, g_t.d) ----
+      // ---- reject: backtrack along dv; cubic through (0, f, gde/alpha) and (alpha, ft, g_t.d) ----
       double gdt = 0.0;
-      for (int j = 0; j < n; ++j) gdt = fma(vec(GT, j), vec(V_D, j), gdt);
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) gdt = fma(gt[j * T], dv[j], gdt);
       const double gd0 = gde / alpha;
       double an = 0.5 * alpha;
       if (ft == ft && gdt == gdt) {
@@ -465,9 +540,12 @@ __global__ void __launch_bounds__(128) adj_lbfgs_kernel(const __grid_constant__ 
         if (hcount > 0) {  // curvature model is bad: restart from steepest descent
           hcount = 0;
           double gg = 0.0;
+#pragma unroll 4
           for (int j = 0; j < n; ++j) {
-            const double gp = proj(X, j, vec(G, j));
-            vec(V_D, j) = -gp;
+            const double xj = x[j * T], gj = g[j * T];
+            double gp = gj;
+            if (bounded && ((xj <= A.lower[j] && gj > 0.0) || (xj >= A.upper[j] && gj < 0.0))) gp = 0.0;
+            dv[j] = -gp;
             gg = fma(gp, gp, gg);
           }
           alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
@@ -481,14 +559,20 @@ __global__ void __launch_bounds__(128) adj_lbfgs_kernel(const __grid_constant__ 
     if (!done) {
       // next trial point x + alpha d (clamped to the box) into the non-current buffer, and the directional derivative
       // along the (projected) segment for the Armijo test
-      const int Xc = 2 * cur, Gc = Xc + 1, Xn = 2 * (cur ^ 1);
+      const double* xc = vecp(2 * cur);
+      const double* gc = xc + (int64_t)n * T;
+      double* xn = vecp(2 * (cur ^ 1));
       double g_step = 0.0;
+#pragma unroll 4
       for (int j = 0; j < n; ++j) {
-        double v = fma(alpha, vec(V_D, j), vec(Xc, j));
-        if (A.lower) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
-        vec(Xn, j) = v;
-        g_step = fma(vec(Gc, j), v - vec(Xc, j), g_step);
+        const double xj = xc[j * T];
+        double v = fma(alpha, dv[j], xj);
+        if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+        t2[j] = v;
+        g_step = fma(gc[j * T], v - xj, g_step);
       }
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) xn[j * T] = t2[j];
       gde = g_step;
       if (!(gde < 0.0)) {  // zero (projected) gradient along the step
         done = true;
@@ -496,9 +580,10 @@ __global__ void __launch_bounds__(128) adj_lbfgs_kernel(const __grid_constant__ 
       }
     }
     if (done) {
+      const double* xf = vecp(2 * cur);
       A.out_loss[pid] = f;
       A.out_iters[pid] = A.debug ? (iter | (reason << 24)) : iter;
-      for (int j = 0; j < n; ++j) A.out_x[pid * n + j] = vec(2 * cur, j);
+      for (int j = 0; j < n; ++j) A.out_x[pid * n + j] = xf[j * T];
       if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + t, 1);
       state = AST_IDLE;
     }
@@ -536,8 +621,9 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   if (rc != SLAM_OK) return rc;
   const int n = kt.P;
   const int64_t total = Nt * (int64_t)restarts;
-  const int threads = 128;
-  int64_t blocks = std::min<int64_t>((int64_t)sms * 2, (total + threads - 1) / threads);
+  const int threads = central == 2 ? kAdjCta : 128;
+  int64_t blocks = std::min<int64_t>((int64_t)sms * (256 / threads), (total + threads - 1) / threads);
+  // (5 + 2 m) double vectors per thread (the adjoint mode keeps its direction in thread-local memory and uses 4 + 2 m)
   const size_t per_thread = (size_t)(5 + 2 * kFdHist) * n * sizeof(double);
   const int64_t T = blocks * threads;
 
@@ -562,7 +648,11 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   A.upper = A.lower ? opts->upper : nullptr;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved; A.ws = ws; A.T = T;
-  if (central == 2) adj_lbfgs_kernel<<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+  if (central == 2) {
+    if (n <= 32) adj_lbfgs_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+    else if (n <= 96) adj_lbfgs_kernel<96><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+    else adj_lbfgs_kernel<SLAM_MAX_PARAMS><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+  }
   else if (central == 1) fd_lbfgs_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
   else fd_lbfgs_kernel<0><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
   cudaError_t e = cudaGetLastError();
