@@ -448,6 +448,21 @@ def micro_benchmarks(engine, peak_flops):
         b.record()
         torch.cuda.synchronize()
         out[label] = {"evals_per_s": 3 * Bs / (a.elapsed_time(b) * 1e-3), "batch": Bs, "params": basis.desc.n_params}
+    # K4b parallel-drive Weyl trajectories (BASELINE configs[3]; pd_playground.py:169-208): N = 10 slices of the 1Q-phase smush
+    # Hamiltonian, R = 5 sub-times each -> one expm + prefix product + c1c2c3 per trajectory point
+    Bt, Nn, Rr = 1 << 18, 10, 5
+    gate = (torch.rand((Bt, 8), device=dev, dtype=torch.float64, generator=g) - 0.5) * 4
+    ax = (torch.rand((Bt, Nn), device=dev, dtype=torch.float64, generator=g) - 0.5) * (4 * math.pi)
+    ay = (torch.rand((Bt, Nn), device=dev, dtype=torch.float64, generator=g) - 0.5) * (4 * math.pi)
+    for _ in range(3):
+        engine.pd_trajectory(gate, ax, ay, 0.1, R=Rr, want_final=False)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        engine.pd_trajectory(gate, ax, ay, 0.1, R=Rr, want_final=False)
+    b.record()
+    torch.cuda.synchronize()
+    out["pd_trajectory_N10_R5"] = {"points_per_s": 3 * Bt * Nn * Rr / (a.elapsed_time(b) * 1e-3), "trajectories": Bt}
     out["smush_k3_adjoint_vs_fd_gradient"] = (out["smush_k3_loss_grad_adjoint"]["evals_per_s"] * (basis.desc.n_params + 1)
                                               / out["smush_k3_loss_only"]["evals_per_s"])
     return out

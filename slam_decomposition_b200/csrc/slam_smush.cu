@@ -1,5 +1,7 @@
 // slam_smush.cu -- K4: templates whose 2Q gate is a time-sliced smush Hamiltonian (forward evaluation),
 // constant-gate lowering, and K4b: the parallel-drive Weyl trajectory.
+#include <cstdlib>
+
 #include "slam_adj1.cuh"
 #include "slam_host.h"
 #include "slam_weyl.cuh"
@@ -125,11 +127,16 @@ int lower_const_smush(const SlamTemplateDesc* d, KTemplate* kt, cudaStream_t st)
 }
 
 // ---- K4b: Weyl trajectory of N smush1q slices, R sub-times each (pd_playground.py:179-208) -----------
-__global__ void __launch_bounds__(128) trajectory_kernel(const double* __restrict__ gate, const double* __restrict__ gx,
-                                                         const double* __restrict__ gy, int N, int Rn, double dt, int flags,
-                                                         double* __restrict__ coords, double* __restrict__ Ufinal, int64_t B) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+// SYNC: phase-locked form (CTA-wide barriers between the exponential and the Weyl step of every trajectory point; all threads
+// run the same N x R loop, padding lanes recompute the last trajectory) -- see fwd1_gate in slam_fwd1.cuh
+template <bool SYNC>
+__global__ void __launch_bounds__(SYNC ? 256 : 128, SYNC ? 1 : 2)
+trajectory_kernel(const double* __restrict__ gate, const double* __restrict__ gx, const double* __restrict__ gy, int N, int Rn,
+                  double dt, int flags, double* __restrict__ coords, double* __restrict__ Ufinal, int64_t B) {
+  const int64_t b0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = b0 < B;
+  if (!SYNC && !valid) return;
+  const int64_t b = valid ? b0 : B - 1;
   const double* gp = gate + b * 8;
   const SmushGate G = smush_gate(gp[0], gp[1], gp[2], gp[3], gp[4], gp[5], gp[6], gp[7]);
   cd P[4][4];  // prefix product of the completed slices, [col][row]
@@ -144,6 +151,7 @@ __global__ void __launch_bounds__(128) trajectory_kernel(const double* __restric
       const double t = (Rn == 1) ? 0.0 : ((q == Rn - 1) ? dt : dt * ((double)q / (double)(Rn - 1)));
       const bool last = (q == Rn - 1);
       if (!coords && !last) continue;
+      if (SYNC) __syncthreads();
       cd Y[4][4];
       smush_slice(G, ax, ay, t, Y);
       cd W[4][4];
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(128) trajectory_kernel(const double* __restric
 #pragma unroll
         for (int r = 0; r < 4; ++r) W[c][r] = P[c][r];
       left_mul(Y, W);
+      if (SYNC) __syncthreads();
       if (coords) {
         cd M[4][4];  // [row][col]
 #pragma unroll
@@ -160,10 +169,12 @@ __global__ void __launch_bounds__(128) trajectory_kernel(const double* __restric
           for (int r = 0; r < 4; ++r) M[r][c] = W[c][r];
         double cc[3];
         weyl_makhlin(M, flags, cc, nullptr);
-        double* o = coords + ((b * N + s) * Rn + q) * 3;
-        o[0] = cc[0];
-        o[1] = cc[1];
-        o[2] = cc[2];
+        if (valid) {
+          double* o = coords + ((b * N + s) * Rn + q) * 3;
+          o[0] = cc[0];
+          o[1] = cc[1];
+          o[2] = cc[2];
+        }
       }
       if (last) {
 #pragma unroll
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(128) trajectory_kernel(const double* __restric
       }
     }
   }
-  if (Ufinal) {
+  if (Ufinal && valid) {
     double* out = Ufinal + b * 32;
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -189,8 +200,14 @@ extern "C" int slam_pd_trajectory(const double* gate, const double* gx, const do
   using namespace slam;
   if (!gate || !gx || !gy || N < 1 || R < 1 || B < 0 || (!coords && !Ufinal)) return SLAM_ERR_INVALID;
   if (B == 0) return SLAM_OK;
-  const unsigned grid = (unsigned)((B + 127) / 128);
-  trajectory_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(gate, gx, gy, N, R, dt, flags, coords, Ufinal, B);
+  const char* e = getenv("SLAM_B200_TRAJ_SYNC");
+  if (e ? atoi(e) != 0 : true) {
+    const unsigned grid = (unsigned)((B + 255) / 256);
+    trajectory_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(gate, gx, gy, N, R, dt, flags, coords, Ufinal, B);
+  } else {
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    trajectory_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(gate, gx, gy, N, R, dt, flags, coords, Ufinal, B);
+  }
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }
