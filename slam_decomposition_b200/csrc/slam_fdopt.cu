@@ -1,8 +1,11 @@
-// slam_fdopt.cu -- K5c: batched quasi-Newton optimiser with FINITE-DIFFERENCE gradients over (target, restart) problems,
-// for the templates whose gates have no closed-form derivative in slam_core.cuh (parameter-bound smush gates,
-// hamiltonian.py:114-182) and the trace-based functionals incl. BasicCostInverse x circuit_fidelity.
+// slam_fdopt.cu -- K5c: batched thread-per-problem quasi-Newton optimiser over (target, restart) problems for the templates
+// the team kernels of slam_core.cuh cannot differentiate in closed form (parameter-bound smush gates,
+// hamiltonian.py:114-182) and the trace-based functionals incl. BasicCostInverse x circuit_fidelity.  Two kernels:
+//   * fd_lbfgs_kernel  -- FINITE-DIFFERENCE gradients (forward or central), sequential control flow per thread;
+//   * adj_lbfgs_kernel -- ANALYTIC adjoint gradients through the smush slices (slam_adj1.cuh), tick-structured and
+//                         phase-locked (bottom of this file); the default for smush templates.
 //
-// This is literally the reference's algorithm class: scipy.optimize.minimize(method="BFGS", jac=None) builds the gradient
+// The finite-difference form is literally the reference's algorithm class: scipy.optimize.minimize(method="BFGS", jac=None) builds the gradient
 // from P forward differences with step sqrt(eps) = 1.49e-8 (src/slam/optimizer.py:270-278).  Here every (target, restart)
 // pair is one thread: P + 1 forward evaluations of the whole template (time-sliced exponentials included) per gradient,
 // limited-memory BFGS with the same Armijo / cautious-update / stopping rules as K5 (slam_lbfgs.cuh), optional box
@@ -47,15 +50,8 @@ struct FdArgs {
   int64_t T;
 };
 
-// out-of-line copy of the adjoint pass: loss + gradient of one workspace vector
-static __device__ __noinline__ double adj1_nl(const KTemplate* kt, const double* p, int64_t stride, const double* V,
-                                              int cost_kind, double* g, int64_t gstride) {
-  StridedParams ps{p, stride};
-  StridedGrad gsw{g, gstride};
-  return adj1_loss_grad(*kt, ps, V, cost_kind, gsw, nullptr);
-}
-
-// phase-locked copy for the tick kernel: every thread of the CTA calls it in the same tick (CTA-wide barriers inside)
+// out-of-line, phase-locked copy of the adjoint pass (loss + gradient of one workspace vector) for the tick kernel: every
+// thread of the CTA calls it in the same tick (CTA-wide barriers inside)
 static __device__ __noinline__ double adj1_nl_sync(const KTemplate* kt, const double* p, int64_t stride, const double* V,
                                                    int cost_kind, double* g, int64_t gstride) {
   StridedParams ps{p, stride};
@@ -63,8 +59,8 @@ static __device__ __noinline__ double adj1_nl_sync(const KTemplate* kt, const do
   return adj1_loss_grad<StridedParams, StridedGrad, true>(*kt, ps, V, cost_kind, gsw, nullptr);
 }
 
-// MODE 0: forward differences (scipy's jac=None), 1: central differences, 2: analytic adjoint gradient through the
-// smush slices (slam_adj1.cuh; GM_SMUSH templates only) -- one backward pass instead of P + 1 forward evaluations
+// MODE 0: forward differences (scipy's jac=None), 1: central differences.  (The analytic adjoint mode, central = 2 at the
+// C ABI, has its own tick-structured kernel below.)
 template <int MODE>
 __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ FdArgs A, const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
@@ -103,16 +99,9 @@ __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ F
     // gradient of buffer xb into buffer gb (fx = objective at xb); returns max |projected g|
     auto grad_at = [&](int xb, int gb, double fx) -> double {
       double gmax = 0.0;
-      if (MODE == 2) {
-        for (int j = 0; j < n; ++j) vec(gb, j) = 0.0;
-        adj1_nl(&kt, &vec(xb, 0), T, A.V + t * 32, A.cost_kind, &vec(gb, 0), T);
-        ++evals;
-      }
       for (int j = 0; j < n; ++j) {
         double gj;
-        if (MODE == 2) {
-          gj = vec(gb, j);
-        } else if (MODE == 1) {
+        if (MODE == 1) {
           gj = (objective_value_nl(&kt, &vec(xb, 0), T, j, h_cen, &ti, A.cost_kind) -
                 objective_value_nl(&kt, &vec(xb, 0), T, j, -h_cen, &ti, A.cost_kind)) / (2.0 * h_cen);
           evals += 2;
@@ -120,7 +109,7 @@ __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ F
           gj = (objective_value_nl(&kt, &vec(xb, 0), T, j, h_fwd, &ti, A.cost_kind) - fx) / h_fwd;
           ++evals;
         }
-        if (MODE != 2) vec(gb, j) = gj;
+        vec(gb, j) = gj;
         double gp = gj;
         if (A.lower) {
           const double xj = vec(xb, j);
