@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SLAM_ABI_VERSION 2
+#define SLAM_ABI_VERSION 3
 #define SLAM_MAX_K 8      /* max 2Q-gate applications per template (reference uses <= 6)       */
 #define SLAM_MAX_SLOTS 40 /* max scalar slots of one 2Q gate (smush1q: 8 + 2T + 1, T <= 15)    */
 #define SLAM_MAX_PARAMS 256
@@ -176,6 +176,17 @@ typedef struct SlamOptOpts {
                   wasted work only: the caller keeps the smallest successful k.                                       */
   const int32_t* solved_in;
   int32_t* solved_out;
+  /* optional circuit-cost constraint (slam_fd_lbfgs_solve only, finite-difference modes), replacing the reference's switch to
+     scipy SLSQP when basis.using_constraints (optimizer.py:259-264; CircuitTemplateV2.set_constraint, basisv2.py:192-203):
+       circuit_cost(x) = sum over 2Q gates of  alpha                      (RiSwap,            custom_gates.py:568-572)
+                                              (|gc| + |gg|) t / (pi/2)    (ConversionGain and its smush form, :208-212, :252-257)
+     enters the objective as the augmented-Lagrangian term (con_mu / 2) max(0, circuit_cost(x) - con_max + lambda / con_mu)^2
+     with one multiplier per (target, restart) problem; the caller runs the outer multiplier iteration.
+       con_mu     penalty weight; 0 = no constraint
+       con_lambda [dev] double[Nt * restarts] multipliers, or NULL (all zero)                                              */
+  double con_max;
+  double con_mu;
+  const double* con_lambda;
 } SlamOptOpts;
 
 void slam_opt_defaults(SlamOptOpts* o);

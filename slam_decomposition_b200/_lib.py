@@ -59,6 +59,9 @@ class SlamOptOpts(C.Structure):
         ("upper", C.c_void_p),
         ("solved_in", C.c_void_p),
         ("solved_out", C.c_void_p),
+        ("con_max", C.c_double),
+        ("con_mu", C.c_double),
+        ("con_lambda", C.c_void_p),
     ]
 
 
@@ -126,7 +129,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.slam_abi_version() != 2:
+    if lib.slam_abi_version() != 3:
         raise SlamError("libslam_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

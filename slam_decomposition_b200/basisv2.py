@@ -117,6 +117,7 @@ class CircuitTemplateV2(_CircuitTemplateBase):
 
     def set_constraint(self, param_max_cost):
         self.constraint_func = {"type": "ineq", "fun": lambda x: param_max_cost - self.circuit_cost(x)}
+        self.constraint_max = float(param_max_cost)  # read by the device optimiser (augmented-Lagrangian term)
         self.using_constraints = True
 
     def remove_constraint(self):

@@ -40,6 +40,8 @@ struct FdArgs {
   double success_threshold, f_stop, gtol, gtol_far, f_far, x0_lo, x0_span;
   const double* lower;
   const double* upper;
+  double con_max, con_mu;    // circuit-cost constraint (FD modes); con_mu = 0: none
+  const double* con_lambda;  // [Nt * restarts] multipliers or null
   double* out_loss;
   double* out_x;
   int32_t* out_iters;
@@ -91,6 +93,11 @@ __global__ void __launch_bounds__(128) fd_lbfgs_kernel(const __grid_constant__ F
     }
     TargetInfo ti;
     target_info_init(ti, A.V + t * 32, A.cost_kind);
+    if (A.con_mu > 0.0) {
+      ti.pen_mu = A.con_mu;
+      ti.pen_max = A.con_max;
+      ti.pen_lambda = A.con_lambda ? A.con_lambda[pid] : 0.0;
+    }
 
     auto f_at = [&](int v) -> double {
       ++evals;
@@ -599,6 +606,8 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true);
   if (rc != SLAM_OK) return rc;
   if (central == 2 && kt.gmode != GM_SMUSH) return SLAM_ERR_UNSUPPORTED;  // closed-form gates: slam_lbfgs_solve
+  if (central == 2 && opts->con_mu != 0.0) return SLAM_ERR_UNSUPPORTED;   // the constraint term is differenced, not adjoint
+  if (opts->con_mu < 0.0) return SLAM_ERR_INVALID;
   if (kt.gmode == GM_DENSE && desc->gate_kind != SLAM_GATE_FIXED) {
     rc = lower_const_smush(desc, &kt, st);
     if (rc != SLAM_OK) return rc;
@@ -635,6 +644,7 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
   A.lower = (opts->lower && opts->upper) ? opts->lower : nullptr;
   A.upper = A.lower ? opts->upper : nullptr;
+  A.con_max = opts->con_max; A.con_mu = opts->con_mu; A.con_lambda = opts->con_lambda;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved; A.ws = ws; A.T = T;
   if (central == 2) {

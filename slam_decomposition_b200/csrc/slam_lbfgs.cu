@@ -77,6 +77,9 @@ extern "C" void slam_opt_defaults(SlamOptOpts* o) {
   o->upper = nullptr;
   o->solved_in = nullptr;
   o->solved_out = nullptr;
+  o->con_max = 0.0;
+  o->con_mu = 0.0;
+  o->con_lambda = nullptr;
 }
 
 extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
@@ -88,6 +91,7 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   if (opts->cost_kind != SLAM_COST_BASIC && opts->cost_kind != SLAM_COST_SQUARE) return SLAM_ERR_UNSUPPORTED;
   if (opts->max_iter < 1 || opts->history < 0 || opts->history > kMaxHist) return SLAM_ERR_INVALID;
   if (desc->n_params < 1) return SLAM_ERR_INVALID;
+  if (opts->con_mu != 0.0) return SLAM_ERR_UNSUPPORTED;  // cost-constrained runs go through slam_fd_lbfgs_solve
   if ((opts->solved_in || opts->solved_out) && !opts->early_exit) return SLAM_ERR_INVALID;
   if (opts->solved_in && !opts->solved_out) return SLAM_ERR_INVALID;  // the chain needs somewhere to propagate to
   if (Nt == 0) return SLAM_OK;

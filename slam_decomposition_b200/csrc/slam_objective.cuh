@@ -18,7 +18,25 @@ struct StridedParams {
 struct TargetInfo {
   const double* V;  // 32 doubles, row-major
   double c[3], g[3];
+  // circuit-cost constraint of this problem (augmented Lagrangian; pen_mu = 0: none)
+  double pen_mu, pen_max, pen_lambda;
 };
+
+// CircuitTemplateV2.circuit_cost (basisv2.py:98-127): RiSwap alpha (custom_gates.py:568-572); ConversionGain and its smush
+// form (|gc| + |gg|) t / (pi/2) (custom_gates.py:208-212, 252-257); every other gate scores 0
+template <class PS>
+__device__ __forceinline__ double circuit_cost(const KTemplate& kt, const PS& ps) {
+  double c = 0.0;
+  for (int g = 0; g < kt.k; ++g) {
+    if (kt.gate_kind == SLAM_GATE_RISWAP) {
+      c += slot_val(kt, ps, g, 0);
+    } else if (kt.gate_kind == SLAM_GATE_CG || kt.gate_kind == SLAM_GATE_SMUSH) {
+      const double tt = slot_val(kt, ps, g, kt.n_slots - 1);
+      c += (fabs(slot_val(kt, ps, g, 2)) + fabs(slot_val(kt, ps, g, 3))) * tt * (1.0 / 1.5707963267948966);
+    }
+  }
+  return c;
+}
 
 __device__ __forceinline__ double generic_cost(const cd R[4][4] /*[col][row]*/, const TargetInfo& t, int kind) {
   if (kind <= SLAM_COST_BASIC_INVERSE) {
@@ -67,6 +85,7 @@ __device__ __forceinline__ double generic_cost(const cd R[4][4] /*[col][row]*/, 
 // Weyl / Makhlin data of the target, needed by the coordinate-based functionals only
 __device__ __forceinline__ void target_info_init(TargetInfo& ti, const double* V, int cost_kind) {
   ti.V = V;
+  ti.pen_mu = ti.pen_max = ti.pen_lambda = 0.0;
   if (cost_kind > SLAM_COST_BASIC_INVERSE) {
     cd M[4][4];
 #pragma unroll
@@ -83,12 +102,18 @@ template <class PS>
 __device__ __forceinline__ double objective_value(const KTemplate& kt, const PS& ps, const TargetInfo& ti, int cost_kind) {
   cd R[4][4];
   fwd1_chain(kt, ps, R);
-  const double c = generic_cost(R, ti, cost_kind);
-  if (cost_kind != SLAM_COST_BASIC_INVERSE) return c;
-  double F = 1.0;
-  if (kt.gate_kind == SLAM_GATE_RISWAP)
-    for (int g = 0; g < kt.k; ++g) F *= slot_val(kt, ps, g, 0);
-  return 1.0 - c * F;
+  double c = generic_cost(R, ti, cost_kind);
+  if (cost_kind == SLAM_COST_BASIC_INVERSE) {
+    double F = 1.0;
+    if (kt.gate_kind == SLAM_GATE_RISWAP)
+      for (int g = 0; g < kt.k; ++g) F *= slot_val(kt, ps, g, 0);
+    c = 1.0 - c * F;
+  }
+  if (ti.pen_mu > 0.0) {
+    const double v = fmax(0.0, circuit_cost(kt, ps) - ti.pen_max + ti.pen_lambda / ti.pen_mu);
+    c = fma(0.5 * ti.pen_mu * v, v, c);
+  }
+  return c;
 }
 
 // parameters of a workspace vector, optionally with one entry shifted: x + h e_j (j < 0: no shift)

@@ -103,6 +103,11 @@ class TemplateOptimizer:
                    (`smush_adjoint`), finite differences -- the reference's own algorithm class -- otherwise;
           "nm"     the derivative-free Nelder-Mead kernel (K5b) for the coordinate-based functionals (Makhlin / Weyl /
                    reduced: piecewise constant after the 8-dp rounding), and when override_method asks for it."""
+        if getattr(self.basis, "using_constraints", False):
+            # the reference switches scipy to SLSQP (optimizer.py:259-264); here: augmented Lagrangian around K5c
+            if ck not in (_lib.COST_BASIC, _lib.COST_SQUARE) or self.override_method == "Nelder-Mead":
+                raise NotImplementedError("cost-constrained templates run with BasicCost / SquareCost and the gradient solver")
+            return "con"
         if self.override_method == "Nelder-Mead":
             return "nm"
         if ck not in (_lib.COST_BASIC, _lib.COST_SQUARE, _lib.COST_BASIC_INVERSE):
@@ -134,8 +139,6 @@ class TemplateOptimizer:
         b = self.basis
         if not isinstance(b, (_CircuitTemplateBase, HamiltonianTemplate)):
             raise NotImplementedError("the device optimizer runs CircuitTemplate / CircuitTemplateV2 / HamiltonianTemplate")
-        if getattr(b, "using_constraints", False):
-            raise NotImplementedError("cost-constrained templates (SLSQP selection, optimizer.py:259-264)")
         if self.override_method not in (None, "BFGS", "L-BFGS-B", "Nelder-Mead"):
             raise NotImplementedError(f"override_method={self.override_method}")
         ck = self._cost_kind()
@@ -151,7 +154,8 @@ class TemplateOptimizer:
         if not k_list:
             raise ValueError("empty spanning range")
         if (self.pipeline and not keep_history and opts.early_exit and len(k_list) > 1
-                and not getattr(b, "using_bounds", False) and self._all_lbfgs(k_list, ck)):
+                and not getattr(b, "using_bounds", False) and not getattr(b, "using_constraints", False)
+                and self._all_lbfgs(k_list, ck)):
             return self._run_chained(V, k_list, opts)
         # persistent workspace: output tables are reused across k and across calls (no allocator churn per sweep)
         ws = self._ws
@@ -222,6 +226,9 @@ class TemplateOptimizer:
                 nm.success_threshold, nm.x0_lo, nm.x0_hi = float(self.success_threshold), lo, hi
                 loss, x, iters = engine.nm_solve(desc, V, R, nm, x0=x0, seed=seed, active=active, evals=evals,
                                                  out=(ws["loss"], x, ws["iters"]))
+            elif solver == "con":
+                loss, x, iters = self._solve_constrained(desc, V, R, opts, ck, x0, seed, active, evals,
+                                                         (ws["loss"], x, ws["iters"]))
             elif solver == "fd":
                 # scipy's BFGS stops at |g| < 1e-5, which on these near-singular landscapes is a loss of 1e-6 .. 1e-8
                 # (the band where the reference's own runs end, scripts/cost_function_comparison.ipynb:118-121).  Here
@@ -271,6 +278,62 @@ class TemplateOptimizer:
             prev = cur_
         return {"best_loss": best_loss.cpu().numpy(), "best_k": best_k.cpu().numpy(), "best_P": best_P.cpu().numpy(),
                 "best_x": best_x, "per_k": per_k, "best_loss_dev": best_loss, "best_k_dev": best_k}
+
+    # ------------------------------------------------------------------------------------------
+    # circuit-cost constraint (CircuitTemplateV2.set_constraint, basisv2.py:192-203; SLSQP in the reference)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _circuit_cost_batch(desc, x: torch.Tensor) -> torch.Tensor:
+        """circuit_cost (basisv2.py:98-127) of every row of x [..., P], on the device, from the descriptor's slot tables."""
+        def slot(g, s_):
+            p = desc.slot_param[g][s_]
+            return x[..., p] if p >= 0 else torch.full(x.shape[:-1], float(desc.slot_const[g][s_]), dtype=x.dtype,
+                                                        device=x.device)
+        c = torch.zeros(x.shape[:-1], dtype=x.dtype, device=x.device)
+        for g in range(desc.k):
+            if desc.gate_kind == _lib.GATE_RISWAP:
+                c = c + slot(g, 0)
+            elif desc.gate_kind in (_lib.GATE_CG, _lib.GATE_SMUSH):
+                c = c + (slot(g, 2).abs() + slot(g, 3).abs()) * slot(g, desc.n_slots - 1) / (np.pi / 2)
+        return c
+
+    def _solve_constrained(self, desc, V, R, opts, ck, x0, seed, active, evals, out):
+        """min cost(U(x), V)  s.t.  circuit_cost(x) <= basis.constraint_max, per (target, restart): augmented Lagrangian
+        with one multiplier per problem; every inner solve is one K5c launch (central differences -- the constraint term is
+        differenced together with the objective, as scipy's SLSQP differences both), warm-started from the previous one.
+        Returns the PURE loss of every restart (+inf where the constraint is violated by more than 1e-7)."""
+        Nt = V.shape[0]
+        P = desc.n_params
+        cmax = float(self.basis.constraint_max)
+        lam = torch.zeros(Nt * R, dtype=torch.float64, device=V.device)
+        mu = 10.0
+        saved = (opts.cost_kind, opts.early_exit, opts.con_mu, opts.con_max, opts.con_lambda, opts.f_far)
+        opts.cost_kind, opts.early_exit, opts.f_far = ck, 0, max(opts.f_far, 1e-4)
+        live = None if active is None else (active != 0)
+        x_start = x0
+        try:
+            for outer in range(8):
+                opts.con_mu, opts.con_max, opts.con_lambda = mu, cmax, lam.data_ptr()
+                loss, x, iters = engine.fd_lbfgs_solve(desc, V, R, opts, x0=x_start, seed=seed, active=active, evals=evals,
+                                                       out=out, central=1)
+                viol = self._circuit_cost_batch(desc, x) - cmax  # [Nt, R]
+                if live is not None:
+                    viol = torch.where(live[:, None], viol, torch.zeros_like(viol))
+                lam = torch.clamp(lam + mu * viol.reshape(-1), min=0.0)
+                if float(viol.clamp(min=0.0).max().item()) <= 1e-9 and outer > 0:
+                    break
+                x_start = x.clone()
+                mu = min(mu * 4.0, 1e7)
+        finally:
+            opts.cost_kind, opts.early_exit, opts.con_mu, opts.con_max, opts.con_lambda, opts.f_far = saved
+        tgt = torch.arange(Nt, dtype=torch.int32, device=V.device).repeat_interleave(R)
+        pure, _, _ = engine.loss_grad(desc, x.reshape(Nt * R, P), V, tgt_idx=tgt, cost_kind=ck, want_grad=False)
+        pure = pure.reshape(Nt, R)
+        pure = torch.where(viol <= 1e-7, pure, torch.full_like(pure, float("inf")))
+        if live is not None:
+            pure = torch.where(live[:, None], pure, torch.full_like(pure, float("inf")))
+        loss.copy_(pure)
+        return loss, x, iters
 
     # ------------------------------------------------------------------------------------------
     # chained sweep: one K5 launch per template size, alternating between two streams

@@ -115,8 +115,9 @@ def test_unsupported_objectives_and_bounds_fail_loudly():
     b2 = CircuitTemplateV2(base_gates=[RiSwapGate])
     b2.build(2)
     b2.set_constraint(1.5)
-    with pytest.raises(NotImplementedError):
-        TemplateOptimizer(b2, BasicCost()).approximate_target_U(O.CNOT)
+    with pytest.raises(NotImplementedError):  # constrained runs: trace functionals with the gradient solver only
+        TemplateOptimizer(b2, BasicCost(), override_method="Nelder-Mead").approximate_target_U(O.CNOT)
+    b2.remove_constraint()
     with pytest.raises(ValueError):
         b2.add_bound("Q99", 1, 0)
     with pytest.raises(ValueError):
@@ -350,3 +351,48 @@ def test_chained_sweep_matches_the_sequential_k_loop():
         k = int(a["cycles"][i])
         tmpl = O.OracleTemplate("riswap", (0.5,), k=k)
         assert abs(O.cost(tmpl.eval(a["Xk"][i, : tmpl.n_params]), V[i], "basic") - a["loss"][i]) < 1e-10
+
+
+def test_cost_constrained_template_against_scipy_slsqp():
+    """CircuitTemplateV2.set_constraint (basisv2.py:192-203): circuit_cost(x) = sum of the RiSwap alphas <= budget.  The
+    reference switches scipy to SLSQP (optimizer.py:259-264); the device path is an augmented Lagrangian around K5c.
+    CX needs alpha0 + alpha1 >= 1 at k = 2, so (a) a budget of 1.2 must still be solved, inside the budget; (b) a budget of
+    0.8 makes CX unreachable and the constrained optimum must match the best of scipy's SLSQP runs on the oracle."""
+    import scipy.optimize as opt
+
+    def make(budget):
+        b = CircuitTemplateV2(n_qubits=2, base_gates=[RiSwapGate])
+        b.build(2)
+        b.spanning_range = range(2, 3)
+        for q in ("Q0", "Q1"):
+            b.add_bound(q, 1.0, 0.0)
+        b.set_constraint(budget)
+        return b
+
+    tmpl = O.OracleTemplate("riswap", ("Q",), k=2)
+    np.random.seed(8)
+    b = make(1.2)
+    d = TemplateOptimizer(b, BasicCost(), override_fail=True, training_restarts=16).approximate_target_U(O.CNOT)
+    assert d.success_label == 1 and d.loss_result <= 1e-9
+    assert b.circuit_cost(d.Xk) <= 1.2 + 1e-7
+    assert abs(O.cost(tmpl.eval(d.Xk), O.CNOT, "basic") - d.loss_result) < 1e-10
+
+    b = make(0.8)
+    d = TemplateOptimizer(b, BasicCost(), override_fail=True, training_restarts=24).approximate_target_U(O.CNOT)
+    assert d.success_label == 0
+    assert b.circuit_cost(d.Xk) <= 0.8 + 1e-7
+    assert abs(O.cost(tmpl.eval(d.Xk), O.CNOT, "basic") - d.loss_result) < 1e-10
+    names = tmpl.names_sorted
+    qi = [names.index("Q0"), names.index("Q1")]
+    bounds = [(0.0, 1.0) if i in qi else (-4 * np.pi, 4 * np.pi) for i in range(len(names))]
+    rng = np.random.default_rng(4)
+    best = np.inf
+    for _ in range(12):
+        x0 = np.array([rng.uniform(lo, hi) for lo, hi in bounds])
+        r = opt.minimize(lambda x: O.cost(tmpl.eval(x), O.CNOT, "basic"), x0, method="SLSQP", bounds=bounds,
+                         constraints={"type": "ineq", "fun": lambda x: 0.8 - x[qi[0]] - x[qi[1]]}, options={"maxiter": 2500})
+        if r.success and r.x[qi[0]] + r.x[qi[1]] <= 0.8 + 1e-7:
+            best = min(best, r.fun)
+    assert np.isfinite(best) and best > 1e-3
+    assert d.loss_result <= best + 1e-5, (d.loss_result, best)
+    assert d.loss_result >= best - 1e-4, (d.loss_result, best)  # (nothing can beat the constrained optimum by more than solver noise)

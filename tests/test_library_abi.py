@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.slam_abi_version() == 2
+    assert lib.slam_abi_version() == 3
     assert lib.slam_status_string(0) == b"ok"
     assert b"invalid" in lib.slam_status_string(-1)
     assert b"unsupported" in lib.slam_status_string(-2)
@@ -44,7 +44,7 @@ def test_struct_layouts_match_the_header():
     # SlamTemplateDesc: 8 int32 + int32[9][6] + int32[8][40] + double[8][40] + double[32]
     assert ctypes.sizeof(_lib.SlamTemplateDesc) == 32 + 9 * 6 * 4 + 8 * 40 * 4 + 8 * 40 * 8 + 32 * 8
     assert _lib.SlamTemplateDesc.slot_const.offset % 8 == 0
-    assert ctypes.sizeof(_lib.SlamOptOpts) == 4 * 4 + 7 * 8 + 2 * 4 + 6 * 8
+    assert ctypes.sizeof(_lib.SlamOptOpts) == 4 * 4 + 7 * 8 + 2 * 4 + 9 * 8
 
 
 def test_opt_defaults_follow_the_reference_constants(lib):
