@@ -124,3 +124,32 @@ def test_shard_ranges_partition_exactly():
             assert rs[0][0] == 0 and rs[-1][1] == n
             assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in rs) - min(b - a for a, b in rs) <= 1
+
+
+def test_circuit_cost_batch_matches_the_per_sample_shim():
+    """The device optimiser's batched circuit_cost (descriptor slot tables, torch) against CircuitTemplateV2.circuit_cost
+    (basisv2.py:98-127) for RiSwap (alpha) and ConversionGain ((|gc| + |gg|) t / (pi/2)) templates."""
+    import torch
+
+    from slam_decomposition_b200.optimizer import TemplateOptimizer
+
+    rng = np.random.default_rng(0)
+    b = CircuitTemplateV2(base_gates=[RiSwapGate])
+    b.build(3)
+    X = rng.uniform(-1, 1, (5, b.desc.n_params))
+    got = TemplateOptimizer._circuit_cost_batch(b.desc, torch.as_tensor(X)).numpy()
+    assert np.allclose(got, [b.circuit_cost(x) for x in X], atol=1e-14)
+
+    def cg(*v):
+        return ConversionGainGate(v[0], v[1], v[2], v[3], 0.5)
+
+    b2 = CircuitTemplateV2(base_gates=[cg], param_vec_expand=[4])
+    b2.build(2)
+    X = rng.uniform(-2, 2, (5, b2.desc.n_params))
+    got = TemplateOptimizer._circuit_cost_batch(b2.desc, torch.as_tensor(X)).numpy()
+    assert np.allclose(got, [b2.circuit_cost(x) for x in X], atol=1e-13)
+    b2.set_constraint(1.5)
+    assert b2.using_constraints and b2.constraint_max == 1.5
+    assert np.isclose(b2.constraint_func["fun"](X[0]), 1.5 - b2.circuit_cost(X[0]))
+    b2.remove_constraint()
+    assert not b2.using_constraints
