@@ -12,8 +12,9 @@ namespace slam {
 // 128-thread CTAs, two per SM (the kernels need ~250 registers).  The phase-locked form that pays off in the coverage kernel
 // (CTA-wide barriers at the layer / gate / slice boundaries, slam_fwd1.cuh) was measured SLOWER here -- 597 vs 661 M evals/s
 // (K1), 170 vs 176 M loss+grad/s (K2) at sqrt(iSWAP) k=3: these kernels read their parameter rows from global memory, and a
-// barrier makes every warp wait for the slowest row -- so SYNC stays off; padding lanes still recompute the last row so that
-// the flag can be flipped for experiments.
+// barrier makes every warp wait for the slowest row; with the rows staged through shared memory first it was still slower
+// (554 vs 656 and 167 vs 184: the warps of a one-shot streaming kernel start in step anyway, the barriers only add waits) --
+// so SYNC stays off; padding lanes still recompute the last row so that the flag can be flipped for experiments.
 constexpr int kSmushCta = 128;
 constexpr bool kSmushSync = false;
 
