@@ -55,9 +55,16 @@ __device__ __forceinline__ void herm_eig4(HermG& A, cd Q[4][4]) {
         if (a2 > 1e-280) {
           const double inv = rsqrt(a2), absh = a2 * inv;
           const double er = h.re * inv, ei = -h.im * inv;  // e^{-i arg h}
-          const double tau = (A.d[q] - A.d[p]) * 0.5 * inv;
-          const double t = copysign(1.0, tau) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
-          const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
+          // rotation angle phi of the real 2x2 problem [[dp, |h|], [|h|, dq]]: cos 2phi = |dq - dp| / r, sin 2phi = 2|h| / r,
+          // r = hypot(dq - dp, 2|h|); half-angle formulas with rsqrt only (the divide + sqrt form of the textbook tangent was
+          // the hottest line of the adjoint kernels: 12 % of the stall samples)
+          const double da = A.d[q] - A.d[p];
+          const double inv_r = rsqrt(fma(da, da, 4.0 * a2));
+          const double u = 0.5 * fma(fabs(da), inv_r, 1.0);  // cos^2 phi, in [1/2, 1]
+          const double ic = rsqrt(u);
+          const double c = u * ic;
+          const double s = copysign(absh * inv_r * ic, da);
+          const double t = s * ic;  // tan phi
           A.d[p] = fma(-t, absh, A.d[p]);
           A.d[q] = fma(t, absh, A.d[q]);
           A.u[hg_idx(p, q)] = mkc(0.0, 0.0);
@@ -112,7 +119,7 @@ __device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, d
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     double s, c;
-    sincos(-0.5 * dt * A.d[a], &s, &c);
+    fast_sincos(-0.5 * dt * A.d[a], &s, &c);
     hp[a] = mkc(c, s);
     ph[a] = mkc(fma(c, c, -(s * s)), 2.0 * c * s);
   }

@@ -198,10 +198,10 @@ __device__ __forceinline__ SmushGate smush_gate(double pa, double pb, double pc,
                                                 double gz1, double gz2) {
   SmushGate G;
   double s, c;
-  sincos(pa, &s, &c); G.ea = mkc(c, -s);
-  sincos(pb, &s, &c); G.eb = mkc(c, -s);
-  sincos(pc, &s, &c); G.ec = mkc(c, -s);
-  sincos(pg, &s, &c); G.eg = mkc(c, -s);
+  fast_sincos(pa, &s, &c); G.ea = mkc(c, -s);
+  fast_sincos(pb, &s, &c); G.eb = mkc(c, -s);
+  fast_sincos(pc, &s, &c); G.ec = mkc(c, -s);
+  fast_sincos(pg, &s, &c); G.eg = mkc(c, -s);
   G.gc = gc; G.gg = gg; G.gz1 = gz1; G.gz2 = gz2;
   return G;
 }
