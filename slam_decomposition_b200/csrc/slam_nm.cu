@@ -95,15 +95,14 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs 
     int ib = 0;
     while (true) {
       // best, worst, second worst
-      int iw = 0, i2 = 0;
+      int iw = 0;
       double fb = DBL_MAX, fw = -DBL_MAX, f2 = -DBL_MAX;
       for (int v = 0; v <= n; ++v) {
         const double f = fs[(int64_t)v * T];
         if (f < fb) { fb = f; ib = v; }
-        if (f > fw) { f2 = fw; i2 = iw; fw = f; iw = v; }
-        else if (f > f2) { f2 = f; i2 = v; }
+        if (f > fw) { f2 = fw; fw = f; iw = v; }
+        else if (f > f2) { f2 = f; }
       }
-      (void)i2;
       // termination (scipy): max |sim[1:] - sim[0]| <= xatol and max |fsim[0] - fsim[1:]| <= fatol
       // (the O(n^2) simplex-diameter scan only runs once the function-value spread has passed its own test)
       double dxmax = DBL_MAX;
