@@ -112,3 +112,38 @@ def test_fast_sincos_matches_libm():
     bad = np.array([np.nan, np.inf])
     lib.slam_selftest_sincos(bad.ctypes.data_as(C.c_void_p), 2, nan_s.ctypes.data_as(C.c_void_p), nan_c.ctypes.data_as(C.c_void_p))
     assert np.all(np.isnan(nan_s)) and np.all(np.isnan(nan_c))
+
+
+def test_ctypes_field_offsets_match_the_c_compiler(tmp_path):
+    """Every field of the three POD structs sits where gcc puts it: a C program including include/slam_b200.h prints
+    offsetof() for each field and the struct sizes; the ctypes mirrors in _lib.py must agree byte for byte."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    structs = {"SlamTemplateDesc": _lib.SlamTemplateDesc, "SlamOptOpts": _lib.SlamOptOpts, "SlamNmOpts": _lib.SlamNmOpts}
+    lines = ["#include <stddef.h>", "#include <stdio.h>", '#include "slam_b200.h"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} size %zu\\n", sizeof({name}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{name} {fname} %zu\\n", offsetof({name}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "offsets.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "offsets"
+    subprocess.run([gcc, "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        sname, field, val = ln.split()
+        cls = structs[sname]
+        if field == "size":
+            assert ctypes.sizeof(cls) == int(val), sname
+        else:
+            assert getattr(cls, field).offset == int(val), (sname, field)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
