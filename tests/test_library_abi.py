@@ -147,3 +147,48 @@ def test_ctypes_field_offsets_match_the_c_compiler(tmp_path):
             assert getattr(cls, field).offset == int(val), (sname, field)
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+
+
+def test_optimiser_option_validation_needs_no_device(lib):
+    """The ABI v2/v3 option fields are validated on the host, before any CUDA call: chained launches need early_exit and a
+    flag array to propagate into; the circuit-cost constraint belongs to slam_fd_lbfgs_solve's finite-difference modes."""
+    from helpers import make_pair
+
+    desc, _ = make_pair("riswap", (0.5,), k=2)
+    fake = ctypes.c_void_p(8)  # never dereferenced: every call below must fail in the argument checks
+
+    def opts():
+        o = _lib.SlamOptOpts()
+        lib.slam_opt_defaults(ctypes.byref(o))
+        return o
+
+    def lbfgs(o):
+        return lib.slam_lbfgs_solve(ctypes.byref(desc), fake, 4, 2, None, desc.n_params, 0, None, ctypes.byref(o), fake, fake,
+                                    fake, None, None)
+
+    def fd(o, mode, d=desc):
+        return lib.slam_fd_lbfgs_solve(ctypes.byref(d), fake, 4, 2, None, d.n_params, 0, None, ctypes.byref(o), mode, fake,
+                                       fake, fake, None, None)
+
+    o = opts()
+    assert (o.solved_in, o.solved_out, o.con_mu, o.con_lambda) == (None, None, 0.0, None)
+    o.solved_in = 8  # without solved_out
+    assert lbfgs(o) == -1
+    o = opts()
+    o.solved_out, o.early_exit = 8, 0
+    assert lbfgs(o) == -1
+    o = opts()
+    o.con_mu = 10.0
+    assert lbfgs(o) == -2   # constrained runs go through slam_fd_lbfgs_solve
+    o = opts()
+    assert fd(o, 3) == -1   # gradient mode out of range
+    assert fd(o, 2) == -2   # the adjoint mode is for parameter-bound smush templates
+    o.con_mu = -1.0
+    assert fd(o, 1) == -1
+    o = opts()
+    o.cost_kind = _lib.COST_MAKHLIN_FUNCTIONAL
+    assert fd(o, 0) == -2   # coordinate-based functionals have no gradient (8-dp rounding)
+    sdesc, _ = make_pair("smush", ("Q", "Q", np.pi / 2, 0.0, "Q", "Q", "Q", "Q", 0.5), k=1, T=2, no_exterior_1q=True)
+    o = opts()
+    o.con_mu = 1.0
+    assert fd(o, 2, sdesc) == -2  # the constraint term is differenced, not adjoint
