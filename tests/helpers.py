@@ -72,3 +72,18 @@ def make_pair(kind="riswap", slots=(0.5,), k=3, T=0, no_exterior_1q=False, vz_on
     assert numeric.size == 0
     assert names == orc.names_sorted, (names, orc.names_sorted)
     return desc, orc
+
+
+def b11_case(kats):
+    """KAT B11 (local_smush_test.ipynb cell 5): the slot tuple of the solved template and its parameter values by name."""
+    t = kats["B11"]["template"]
+    slots = tuple(t["slots"])
+    vals = {}
+    p = 0
+    for tri in kats["B11"]["u3_triples"]:
+        for v in tri:
+            vals[f"P{p}"] = v
+            p += 1
+    for q, v in enumerate(list(kats["B11"]["gx"]) + list(kats["B11"]["gy"])):
+        vals[f"Q{q}"] = v
+    return slots, t["k"], t["T"], vals

@@ -171,3 +171,34 @@ def test_drive_amplitude_search_with_makhlin_cost():
     U = basis.eval(d.Xk)
     assert abs(O.cost(U, O.CNOT, "makhlin_euclidean") - d.loss_result) < 3e-8
     assert d.loss_result < 5e-3 and np.allclose(O.fold_c1(np.array(O.c1c2c3(U))), (0.5, 0.0, 0.0), atol=5e-3)
+
+
+def test_b11_reference_recorded_smush_solution_on_device():
+    """KAT B11 (scripts/local_smush_test.ipynb cell 5): the reference's own solved smush circuit, T = 5 slices between
+    exterior U3 layers, through K1 (unitary vs oracle at 1e-10), K3 (coordinates), the fused cost functional and K5b's
+    objective (MakhlinFunctionalCost vs CX == 0.0 exactly, as the reference logged 'Best Loss=0.0')."""
+    import json
+    import os
+
+    from helpers import b11_case
+    from slam_decomposition_b200 import _lib
+    from slam_decomposition_b200.cost_function import MakhlinFunctionalCost
+
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kats.json")))
+    slots, k, T, vals = b11_case(kats)
+    desc, orc = make_pair("smush", slots, k=k, T=T)
+    x = np.array([[vals[n] for n in orc.names_sorted]])
+    U = engine.template_eval(desc, _dev(x))
+    assert np.abs(U.cpu().numpy()[0] - orc.eval(x[0])).max() < TOL_U
+    c, g = engine.weyl(U, round8=True, want_g=True)
+    c = c[0].tolist()
+    assert c[0] == kats["B11"]["c1"] and 0 <= c[1] < kats["B11"]["c2_c3_below"] and 0 <= c[2] < kats["B11"]["c2_c3_below"]
+    assert tuple(c) == O.c1c2c3(orc.eval(x[0]))
+    assert tuple(abs(v) for v in g[0].tolist()) == (0.0, 0.0, 1.0)
+    assert MakhlinFunctionalCost().unitary_fidelity(U[0].cpu().numpy(), O.CNOT) == kats["B11"]["makhlin_functional_vs_CX"] == 0.0
+    # K5b objective: Nelder-Mead started AT the recorded solution can only report a loss <= f(x0) = 0.0, and the
+    # functional is non-negative, so the kernel's own evaluation of the recorded point must be exactly 0.0
+    nm = engine.nm_defaults()
+    nm.cost_kind, nm.max_iter, nm.early_exit = _lib.COST_MAKHLIN_FUNCTIONAL, 1, 0
+    loss, _, _ = engine.nm_solve(desc, _dev(O.CNOT[None].astype(np.complex128)), 1, nm, x0=_dev(x[None]))
+    assert loss.item() == 0.0

@@ -61,24 +61,61 @@ def test_haar_batch_unrounded():
     assert np.abs(cf - O.fold_c1(co)).max() < TOL
 
 
-def test_degenerate_and_locally_equivalent_inputs():
-    """Degenerate spectra (CNOT/iSWAP/SWAP/identity classes) dressed with random local gates."""
+def _dress(rng, M, n):
+    out = []
+    for _ in range(n):
+        k1 = np.kron(O.u3(*rng.uniform(0, 7, 3)), O.u3(*rng.uniform(0, 7, 3)))
+        k2 = np.kron(O.u3(*rng.uniform(0, 7, 3)), O.u3(*rng.uniform(0, 7, 3)))
+        out.append(np.exp(1j * rng.uniform(0, 7)) * (k1 @ M @ k2))
+    return out
+
+
+CLASSES = {  # chamber points every basis gate of this domain sits on (parallel_drive_volume.py:91-96 and the chamber corners)
+    "I": (0.0, 0.0, 0.0), "CNOT": (0.5, 0.0, 0.0), "SWAP": (0.5, 0.5, 0.5), "iSWAP": (0.5, 0.5, 0.0),
+    "sqiSWAP": (0.25, 0.25, 0.0), "B": (0.5, 0.25, 0.0), "sqCNOT": (0.25, 0.0, 0.0), "sqB": (0.25, 0.125, 0.0),
+}
+
+
+def test_degenerate_and_locally_equivalent_inputs(capsys):
+    """Degenerate spectra (identity / CNOT / SWAP / iSWAP / sqrt-iSWAP / B / sqCNOT / sqB classes) dressed with random
+    local gates and a global phase: the folded coordinates must equal the class point to north_star's 1e-10 (the
+    eigenphases of the unitary m = U_B^T U_B are perfectly conditioned; the joint-Jacobi kernel reaches ~1e-15 here)."""
     rng = np.random.default_rng(1)
-    base = [np.eye(4), O.CNOT, O.SWAP, O.ISWAP, O.riswap(0.5), O.berkeley(), O.conversion_gain(0, 0, np.pi / 4, np.pi / 4, 0.5)]
-    Us, ref = [], []
-    for M in base:
-        cm = O.fold_c1(O.c1c2c3_raw(M))
-        for _ in range(50):
-            k1 = np.kron(O.u3(*rng.uniform(0, 7, 3)), O.u3(*rng.uniform(0, 7, 3)))
-            k2 = np.kron(O.u3(*rng.uniform(0, 7, 3)), O.u3(*rng.uniform(0, 7, 3)))
-            Us.append(np.exp(1j * rng.uniform(0, 7)) * (k1 @ M @ k2))
-            ref.append(cm)
-    c, g = _coords(np.stack(Us), fold=True)
-    ref = np.array(ref)
-    # on chamber faces the representative (c1 vs 1-c1 is folded; c3=0 plane) is unique after folding
-    assert np.abs(c - ref).max() < 1e-7  # degenerate points: sqrt-type sensitivity of the *reference* itself
-    go = O.g1g2g3_raw(np.stack(Us))
-    assert np.abs(g - go).max() < TOL
+    base = {"I": np.eye(4), "CNOT": O.CNOT, "SWAP": O.SWAP, "iSWAP": O.ISWAP, "sqiSWAP": O.riswap(0.5), "B": O.berkeley(),
+            "sqCNOT": O.conversion_gain(0, 0, np.pi / 4, np.pi / 4, 0.5), "sqB": O.conversion_gain(0, 0, 3 * np.pi / 8, np.pi / 8, 0.5)}
+    Us, ref, who = [], [], []
+    for name, M in base.items():
+        assert np.abs(O.fold_c1(O.c1c2c3_raw(M)) - np.array(CLASSES[name])).max() < 1e-15, name
+        for U in _dress(rng, M, 200):
+            Us.append(U)
+            ref.append(CLASSES[name])
+            who.append(name)
+    Us, ref, who = np.stack(Us), np.array(ref), np.array(who)
+    c, g = _coords(Us, fold=True)
+    err = np.abs(c - ref).max(axis=1)
+    with capsys.disabled():
+        print("\n  max |dc| per class: " + ", ".join(f"{n}={err[who == n].max():.1e}" for n in base))
+    assert err.max() < TOL
+    assert np.abs(c - O.fold_c1(O.c1c2c3_raw(Us))).max() < TOL
+    assert np.abs(g - O.g1g2g3_raw(Us)).max() < TOL
+
+
+def test_near_degenerate_inputs_along_chamber_edges():
+    """Class points offset by 1e-12 .. 1e-4 along every chamber edge direction (near-degenerate eigenphase pairs, and
+    points just outside the chamber that map back in), dressed with local gates: device vs oracle at 1e-10."""
+    rng = np.random.default_rng(3)
+    dirs = [(1, 0, 0), (1, 1, 0), (1, 1, 1), (0, 1, 0), (0, 1, 1), (0, 0, 1)]
+    dirs = dirs + [tuple(-v for v in d) for d in dirs]
+    Us = []
+    for p in CLASSES.values():
+        for eps in (1e-12, 1e-9, 1e-8, 1e-7, 1e-6, 1e-4):
+            for d in dirs:
+                q = np.array(p) + eps * np.array(d)
+                Us.extend(_dress(rng, O.canonical_gate(*q), 4))
+    Us = np.stack(Us)
+    c, g = _coords(Us, fold=True)
+    assert np.abs(c - O.fold_c1(O.c1c2c3_raw(Us))).max() < TOL
+    assert np.abs(g - O.g1g2g3_raw(Us)).max() < TOL
 
 
 def test_template_outputs_b1_b2():

@@ -69,6 +69,24 @@ def test_b5b_makhlin_functional_bit_pattern():
     assert O.J_T_LI(O.SWAP, O.SWAP) == 0.0
 
 
+def test_b11_smush_template_solution_recorded_by_the_reference():
+    """The only reference-held record of the smush Hamiltonian path: the solved circuit drawn in
+    scripts/local_smush_test.ipynb cell 5 (MakhlinFunctionalCost vs CX: 'Best Loss=0.0', 'Cost: 1.0')."""
+    from helpers import b11_case
+
+    slots, k, T, vals = b11_case(KATS)
+    tmpl = O.OracleTemplate("smush", slots, k=k, T=T)
+    U = tmpl.eval([vals[n] for n in tmpl.names_sorted])
+    assert np.abs(U @ U.conj().T - np.eye(4)).max() < 1e-13
+    assert O.J_T_LI(O.CNOT, U) == KATS["B11"]["makhlin_functional_vs_CX"] == 0.0
+    assert O.cost(U, O.CNOT, "makhlin_functional") == 0.0
+    c = O.c1c2c3(U)
+    assert c[0] == KATS["B11"]["c1"] and 0 <= c[1] < KATS["B11"]["c2_c3_below"] and 0 <= c[2] < KATS["B11"]["c2_c3_below"]
+    # circuit cost of the smush gate: (|gc| + |gg|) t / (pi/2)  (custom_gates.py:252-257)
+    gc, gg, t = slots[2], slots[3], slots[-1]
+    assert (abs(gc) + abs(gg)) * t / (np.pi / 2) == KATS["B11"]["circuit_cost"]
+
+
 def test_b10_makhlin_invariants():
     gates = {"I": np.eye(4), "CNOT": O.CNOT, "SWAP": O.SWAP, "iSWAP": O.ISWAP, "sqrt_iSWAP": O.riswap(0.5)}
     for name, G in gates.items():
