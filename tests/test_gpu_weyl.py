@@ -70,6 +70,23 @@ def _dress(rng, M, n):
     return out
 
 
+def _assert_matches_oracle_or_class(Us, c, who=None):
+    """Device vs oracle at TOL.  weylchamber's own algorithm (which the oracle restates literally) is unstable exactly
+    at the SWAP corner: all four eigenphases sit on its `two_S <= -0.5` branch point and round-off can send it to the
+    out-of-chamber representative (1.5, -0.5, 0.5) (the reference works around this, speed_limit_pass.py:369-377).
+    Rows where the oracle leaves the chamber are therefore checked against the invariants instead: the device
+    coordinates must lie in the chamber and canonical_gate(c) must have the Makhlin invariants of U."""
+    co = O.fold_c1(O.c1c2c3_raw(Us))
+    bad = np.abs(c - co).max(axis=1) >= TOL
+    for i in np.nonzero(bad)[0]:
+        in_chamber = -1e-12 <= co[i, 2] <= co[i, 1] + 1e-12 and co[i, 1] <= co[i, 0] + 1e-12 and co[i, 0] <= 0.5 + 1e-12
+        assert not in_chamber, (i, c[i], co[i])  # a genuine disagreement
+        assert -1e-12 <= c[i, 2] <= c[i, 1] + 1e-12 <= c[i, 0] + 2e-12 <= 0.5 + 3e-12, c[i]
+        assert np.abs(np.array(O.g1g2g3_raw(O.canonical_gate(*c[i]))) - np.array(O.g1g2g3_raw(Us[i]))).max() < 1e-9
+        assert np.abs(c[i] - 0.5).max() < 1e-3, c[i]  # only ever near the SWAP corner
+    return int(bad.sum())
+
+
 CLASSES = {  # chamber points every basis gate of this domain sits on (parallel_drive_volume.py:91-96 and the chamber corners)
     "I": (0.0, 0.0, 0.0), "CNOT": (0.5, 0.0, 0.0), "SWAP": (0.5, 0.5, 0.5), "iSWAP": (0.5, 0.5, 0.0),
     "sqiSWAP": (0.25, 0.25, 0.0), "B": (0.5, 0.25, 0.0), "sqCNOT": (0.25, 0.0, 0.0), "sqB": (0.25, 0.125, 0.0),
@@ -96,7 +113,7 @@ def test_degenerate_and_locally_equivalent_inputs(capsys):
     with capsys.disabled():
         print("\n  max |dc| per class: " + ", ".join(f"{n}={err[who == n].max():.1e}" for n in base))
     assert err.max() < TOL
-    assert np.abs(c - O.fold_c1(O.c1c2c3_raw(Us))).max() < TOL
+    _assert_matches_oracle_or_class(Us, c)
     assert np.abs(g - O.g1g2g3_raw(Us)).max() < TOL
 
 
@@ -114,7 +131,7 @@ def test_near_degenerate_inputs_along_chamber_edges():
                 Us.extend(_dress(rng, O.canonical_gate(*q), 4))
     Us = np.stack(Us)
     c, g = _coords(Us, fold=True)
-    assert np.abs(c - O.fold_c1(O.c1c2c3_raw(Us))).max() < TOL
+    _assert_matches_oracle_or_class(Us, c)
     assert np.abs(g - O.g1g2g3_raw(Us)).max() < TOL
 
 
