@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SLAM_ABI_VERSION 3
+#define SLAM_ABI_VERSION 4
 #define SLAM_MAX_K 8      /* max 2Q-gate applications per template (reference uses <= 6)       */
 #define SLAM_MAX_SLOTS 40 /* max scalar slots of one 2Q gate (smush1q: 8 + 2T + 1, T <= 15)    */
 #define SLAM_MAX_PARAMS 256
@@ -160,8 +160,9 @@ typedef struct SlamOptOpts {
   int32_t reserved;
   double* trace_loss;
   double* trace_x;
-  /* optional box bounds, [dev] double[P] each (NULL = unbounded): projected L-BFGS, replacing the reference's
-     switch to scipy L-BFGS-B when basis.using_bounds (optimizer.py:257-258, basisv2.py:174-190); +-inf allowed.   */
+  /* optional box bounds, [dev] double[P] each: projected L-BFGS, replacing the reference's switch to scipy L-BFGS-B
+     when basis.using_bounds (optimizer.py:257-258, basisv2.py:174-190).  Both arrays or neither (SLAM_ERR_INVALID
+     otherwise); a side without a bound is +-inf.  Initial points are clamped into the box.                           */
   const double* lower;
   const double* upper;
   /* optional chaining of launches over ascending template sizes k (slam_lbfgs_solve only), so that the launch for k+1 can
@@ -187,6 +188,24 @@ typedef struct SlamOptOpts {
   double con_max;
   double con_mu;
   const double* con_lambda;
+  /* optional per-TARGET reduction over restarts AND over the chained launches of ascending template sizes (slam_lbfgs_solve
+     only) -- the merge the reference does on the host, optimizer.py:283-303: "the smallest k that reached the threshold, else
+     the lowest loss seen".  Every retired restart issues one fire-and-forget 64-bit atomicMin on best_key[target] with
+         bit 63 = loss >= success_threshold | bits 62-59 = k if below the threshold, else 0 | bits 58-12 = top 47 bits of
+         the loss (order preserving) | bits 11-8 = k | bits 7-0 = restart
+     so the minimum identifies the winning (k, restart); slam_best_gather() then copies the winner's loss and parameters out
+     of the per-restart tables.  Non-finite losses never enter.  Needs restarts <= 256 and k <= 15.
+       best_key [dev] uint64[Nt], caller initialises to all ones (0xFFFF...F = no result yet)                            */
+  unsigned long long* best_key;
+  /* launch tuning of slam_lbfgs_solve, 0 = automatic (explicit fields, so A/B measurements need no environment variables):
+       tune_lanes       lanes per problem, 2 or 4
+       tune_sm_threads  register class for canonical templates with P <= 24: 512 (16 warps/SM, 128 registers) or 384
+       tune_hist_min    smallest history length the automatic choice may shrink to in order to fit more teams
+       tune_max_teams   cap on the teams (problems in flight) per SM                                                     */
+  int32_t tune_lanes;
+  int32_t tune_sm_threads;
+  int32_t tune_hist_min;
+  int32_t tune_max_teams;
 } SlamOptOpts;
 
 void slam_opt_defaults(SlamOptOpts* o);
@@ -195,15 +214,31 @@ void slam_opt_defaults(SlamOptOpts* o);
  *   V          [dev] double[Nt,32] targets
  *   x0         [dev] double[Nt, restarts, ldx0] or NULL (then Philox4x32-10 keyed by seed)
  *   active     [dev] int32[Nt] or NULL: targets with active[t] == 0 are skipped (already solved)
- *   out_loss   [dev] double[Nt, restarts]   final loss of every restart (+inf if skipped/aborted)
+ *   out_loss   [dev] double[Nt, restarts]   final loss of every restart (DBL_MAX = skipped: target inactive / already
+ *                                           solved; NaN = the objective went non-finite)
  *   out_x      [dev] double[Nt, restarts, P] final parameters of every restart
  *   out_iters  [dev] int32 [Nt, restarts]   L-BFGS iterations used
+
  *   out_evals  [dev] int64 [1] or NULL      += number of loss+grad evaluations performed
  */
 int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
                      const double* x0, int64_t ldx0, uint64_t seed, const int32_t* active,
                      const SlamOptOpts* opts, double* out_loss, double* out_x, int32_t* out_iters,
                      unsigned long long* out_evals, void* stream);
+
+/*
+ * Winners of the per-target reduction (SlamOptOpts.best_key) copied out of the per-restart tables of the chained launches:
+ * for target t with key (k, r): best_loss[t] = loss_k[t, r], best_k[t] = k, best_P[t] = P_k, best_x[t, :P_k] = x_k[t, r, :]
+ * (zero padded to ldx); targets without a finite result get (+inf, -1, 0, zeros).  Replaces the host-side bookkeeping of
+ * optimizer.py:283-303 (`best_result`, `best_Xk`, `best_cycles`).
+ *   k_of_size, P_of_size  HOST int32[n_sizes]: template size k and parameter count of every launch of the chain
+ *   loss_of_size, x_of_size  HOST arrays of n_sizes [dev] pointers: out_loss [Nt, restarts] and out_x [Nt, restarts, P] of
+ *                            that launch
+ */
+int slam_best_gather(const unsigned long long* best_key, int64_t Nt, int32_t restarts, int32_t n_sizes,
+                     const int32_t* k_of_size, const int32_t* P_of_size, const double* const* loss_of_size,
+                     const double* const* x_of_size, double* best_loss, int32_t* best_k, int32_t* best_P, double* best_x,
+                     int64_t ldx, void* stream);
 
 /*
  * K5c Batched L-BFGS with FINITE-DIFFERENCE gradients over the generic forward objective: the reference's own algorithm

@@ -1,6 +1,6 @@
-"""A/B harness for the K5 launch configuration (lanes per problem, exact-length kernels, history storage, history
-length): runs the headline sweep (Haar targets x 16 restarts onto sqCNOT templates k = 1..6) under each setting of the
-SLAM_B200_LBFGS_* environment overrides and prints per-k kernel time, evaluations and the solved fraction.
+"""A/B harness for the K5 launch configuration: runs the headline sweep (Haar targets x 16 restarts onto sqCNOT templates
+k = 1..6, chained launches) under each setting of the explicit SlamOptOpts.tune_* fields and prints the sweep time, the
+per-k charged time, evaluations and the solved fraction.
 Usage: python scripts/lbfgs_config_sweep.py [targets] [config-name ...]"""
 import json
 import os
@@ -18,17 +18,13 @@ from slam_decomposition_b200.optimizer import TemplateOptimizer
 from slam_decomposition_b200.utils.gates.custom_gates import ConversionGainGate
 
 CONFIGS = {
-    "x384": {},
-    "x384_f32": {"SLAM_B200_LBFGS_HIST": "0"},
-    "generic": {"SLAM_B200_LBFGS_EXACT": "0"},
-    "x512_m6": {"SLAM_B200_LBFGS_MAXT": "512", "SLAM_B200_LBFGS_MMIN": "6"},
-    "x512_m5": {"SLAM_B200_LBFGS_MAXT": "512", "SLAM_B200_LBFGS_MMIN": "5"},
-    "x512_m4": {"SLAM_B200_LBFGS_MAXT": "512", "SLAM_B200_LBFGS_MMIN": "4"},
-    "x512_m3": {"SLAM_B200_LBFGS_MAXT": "512", "SLAM_B200_LBFGS_MMIN": "3"},
-    "lpp2_m3": {"SLAM_B200_LBFGS_LPP": "2", "SLAM_B200_LBFGS_MMIN": "3"},
+    "auto": {},
+    "m4": {"tune_hist_min": 4},
+    "w12": {"tune_sm_threads": 384},
+    "lpp2": {"tune_lanes": 2},
+    "teams96": {"tune_max_teams": 96},
+    "nopipe": {"_pipeline": False},
 }
-KEYS = ("SLAM_B200_LBFGS_LPP", "SLAM_B200_LBFGS_EXACT", "SLAM_B200_LBFGS_HIST", "SLAM_B200_LBFGS_MMIN", "SLAM_B200_LBFGS_TEAMS",
-        "SLAM_B200_LBFGS_MAXT")
 
 
 def main():
@@ -36,42 +32,57 @@ def main():
     names = sys.argv[2:] or list(CONFIGS)
     dev = engine.require_cuda()
     basis = CircuitTemplate(base_gates=[ConversionGainGate(*bench.SQCNOT)], maximum_span_guess=6)
-    opt = TemplateOptimizer(basis=basis, objective=BasicCost(), override_fail=True, training_restarts=16)
     V = torch.as_tensor(bench.haar_targets(Nt, 42), device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     out = {}
     for name in names:
-        for key in KEYS:
-            os.environ.pop(key, None)
-        os.environ.update(CONFIGS[name])
+        cfg = dict(CONFIGS[name])
+        opt = TemplateOptimizer(basis=basis, objective=BasicCost(), override_fail=True, training_restarts=16)
+        opt.pipeline = cfg.pop("_pipeline", True)
+        opt.tune = cfg
         np.random.seed(7)
-        opt._run_batch(V, range(1, 7))  # warm-up
+        for _ in range(2):
+            opt._run_batch(V, range(1, 7))  # warm-up
         torch.cuda.synchronize()
         engine.LBFGS_EVENTS = []
+        engine.LBFGS_SPANS = []
         opt.launch_evals = []
-        reps = 2
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        reps = 3
+        tot = 0.0
         for _ in range(reps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             res = opt._run_batch(V, range(1, 7))
-        e1.record()
-        torch.cuda.synchronize()
-        ev, le = engine.LBFGS_EVENTS, list(opt.launch_evals)
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        ev, le, spans = engine.LBFGS_EVENTS, list(opt.launch_evals), engine.LBFGS_SPANS
         engine.LBFGS_EVENTS = None
+        engine.LBFGS_SPANS = None
         per_k = {}
-        for (k, a, b), (_, n) in zip(ev, le):
+        per_sweep = len(ev) // reps
+        for idx, ((k, a, b), (_, n)) in enumerate(zip(ev, le)):
             d = per_k.setdefault(k, [0.0, 0])
-            d[0] += a.elapsed_time(b) / reps
+            if spans:
+                prev_end = spans[idx // per_sweep][0] if idx % per_sweep == 0 else ev[idx - 1][2]
+                d[0] += max(prev_end.elapsed_time(b), 0.0) / reps
+            else:
+                d[0] += a.elapsed_time(b) / reps
             d[1] += n / reps
         solved = float((res["best_loss"] <= 1e-10).mean())
         mean_k = float(res["best_k"].astype(np.float64).mean())
-        total = e0.elapsed_time(e1) / reps
-        kern = sum(v[0] for v in per_k.values())
-        line = " ".join(f"k{k}: {v[0]:6.2f} ms {v[1] / 1e6:6.2f} Mev {v[1] / v[0] / 1e6:5.2f} Gev/s |" for k, v in sorted(per_k.items()))
-        print(f"{name:20s} sweep {total:7.2f} ms  kernels {kern:7.2f} ms  solved {solved:.5f} mean_k {mean_k:.4f}\n    {line}", flush=True)
-        out[name] = {"sweep_ms": total, "kernel_ms": kern, "solved": solved, "mean_k": mean_k,
+        total = tot / reps
+        kern = (sum(a.elapsed_time(b) for a, b in spans) / reps) if spans else sum(v[0] for v in per_k.values())
+        evals = sum(v[1] for v in per_k.values())
+        line = " ".join(f"k{k}: {v[0]:6.2f} ms {v[1] / 1e6:6.2f} Mev |" for k, v in sorted(per_k.items()))
+        print(f"{name:12s} sweep {total:7.2f} ms  kernels {kern:7.2f} ms  {evals / total / 1e6:7.3f} Gev/s  solved {solved:.5f} "
+              f"mean_k {mean_k:.4f}\n    {line}", flush=True)
+        out[name] = {"sweep_ms": total, "kernel_ms": kern, "solved": solved, "mean_k": mean_k, "evals": evals,
                      "per_k": {k: {"ms": v[0], "evals": v[1]} for k, v in per_k.items()}}
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/lbfgs_config_sweep.json", "w") as fh:
+    tag = os.environ.get("SWEEP_TAG", "")
+    with open(f"gpurun_out/lbfgs_config_sweep{tag}.json", "w") as fh:
         json.dump(out, fh, indent=1)
 
 

@@ -15,6 +15,7 @@ GATE_RISWAP, GATE_CG, GATE_SMUSH, GATE_SMUSH_1QPHASE, GATE_FIXED = range(5)
 (COST_BASIC, COST_SQUARE, COST_BASIC_INVERSE, COST_MAKHLIN_FUNCTIONAL, COST_MAKHLIN_EUCLIDEAN, COST_WEYL_EUCLIDEAN,
  COST_BASIC_REDUCED, COST_SQUARE_REDUCED) = range(8)
 WEYL_FOLD, WEYL_ROUND8 = 1, 2
+ABI_VERSION = 4
 
 import os
 
@@ -62,6 +63,11 @@ class SlamOptOpts(C.Structure):
         ("con_max", C.c_double),
         ("con_mu", C.c_double),
         ("con_lambda", C.c_void_p),
+        ("best_key", C.c_void_p),
+        ("tune_lanes", C.c_int32),
+        ("tune_sm_threads", C.c_int32),
+        ("tune_hist_min", C.c_int32),
+        ("tune_max_teams", C.c_int32),
     ]
 
 
@@ -97,6 +103,7 @@ _PROTOS = {
     "slam_opt_defaults": (None, [C.POINTER(SlamOptOpts)]),
     "slam_lbfgs_solve": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_uint64, _P,
                                    C.POINTER(SlamOptOpts), _P, _P, _P, _P, _P]),
+    "slam_best_gather": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "slam_fd_lbfgs_solve": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_uint64, _P,
                                       C.POINTER(SlamOptOpts), C.c_int32, _P, _P, _P, _P, _P]),
     "slam_nm_defaults": (None, [C.POINTER(SlamNmOpts)]),
@@ -129,7 +136,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.slam_abi_version() != 3:
+    if lib.slam_abi_version() != ABI_VERSION:
         raise SlamError("libslam_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

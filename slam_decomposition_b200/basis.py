@@ -21,6 +21,25 @@ from .hamiltonian import Hamiltonian
 from .utils.gates.custom_gates import RiSwapGate
 
 
+class _Cycler:
+    """``itertools.cycle`` with a readable position.  The reference creates its gate / edge cycles ONCE in ``__init__``
+    (basis.py:68-72, basisv2.py:61-64), so they keep advancing across successive ``build()`` calls: with more than one base
+    gate the sequence a build sees depends on how many gates earlier builds consumed.  The position is exposed so that the
+    optimiser's probing builds (which the reference does not do) can be undone."""
+
+    def __init__(self, items):
+        self.items = list(items)
+        self.pos = 0
+
+    def __next__(self):
+        v = self.items[self.pos % len(self.items)]
+        self.pos += 1
+        return v
+
+    def __iter__(self):
+        return self
+
+
 class _CircuitTemplateBase(VariationalTemplate):
     """Shared machinery of CircuitTemplate / CircuitTemplateV2: device evaluation of the built circuit."""
 
@@ -53,6 +72,19 @@ class _CircuitTemplateBase(VariationalTemplate):
         self.circuit = TemplateCircuit(self.n_qubits)
         self._p_index = 0
         self._q_index = 0
+
+    def _init_cycles(self):
+        self.gate_2q_base = _Cycler(self._base_gates)
+        self.gate_2q_edges = _Cycler([_Cycler(e) for e in self._edge_params])
+
+    def cycle_state(self):
+        """Positions of the gate / edge cycles (see _Cycler)."""
+        return (self.gate_2q_base.pos, self.gate_2q_edges.pos, tuple(c.pos for c in self.gate_2q_edges.items))
+
+    def set_cycle_state(self, state):
+        self.gate_2q_base.pos, self.gate_2q_edges.pos = state[0], state[1]
+        for c, pos in zip(self.gate_2q_edges.items, state[2]):
+            c.pos = pos
 
     def _next_1q(self, n):
         out = [Parameter(f"P{self._p_index + j}") for j in range(n)]
@@ -140,13 +172,9 @@ class CircuitTemplate(_CircuitTemplateBase):
             self.spanning_range = range(1, maximum_span_guess + 1)
             self.coverage = None
         super().__init__(preseed=preseed, use_polytopes=use_polytopes)
+        self._init_cycles()
         self._reset()
         self.trotter = False
-
-    def _reset(self):
-        super()._reset()
-        self.gate_2q_base = cycle(self._base_gates)
-        self.gate_2q_edges = cycle([cycle(e) for e in self._edge_params])
 
     def get_spanning_range(self, target_u):
         return self.spanning_range

@@ -5,7 +5,6 @@ that receives fresh ``Q{j}`` parameters on every repetition (continuous 2Q searc
 from __future__ import annotations
 
 from inspect import signature
-from itertools import cycle
 
 import numpy as np
 
@@ -39,13 +38,9 @@ class CircuitTemplateV2(_CircuitTemplateBase):
             self.spanning_range = range(1, maximum_span_guess + 1)
             self.coverage = None
         super().__init__(preseed=preseed, use_polytopes=use_polytopes)
+        self._init_cycles()
         self._reset()
         self.trotter = False
-
-    def _reset(self):
-        super()._reset()
-        self.gate_2q_base = cycle(self._base_gates)
-        self.gate_2q_edges = cycle([cycle(e) for e in self._edge_params])
 
     def get_spanning_range(self, target_u):
         return self.spanning_range

@@ -36,21 +36,28 @@ def _stale() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into one shared library (no torch dependency)."""
+def build(force: bool = False, verbose: bool = False, defines=(), out: Path | None = None) -> Path:
+    """Compile every CUDA source for sm_100a into one shared library (no torch dependency).
+    `defines` / `out`: A/B builds with extra -D macros into another file (loaded through SLAM_B200_LIB)."""
+    if out is not None:
+        return _build_to(Path(out), list(defines), verbose)
     if not force and not _stale():
         return LIB
+    return _build_to(LIB, [], verbose)
+
+
+def _build_to(LIB: Path, defines, verbose: bool) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libslam_b200.so")
-    objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = PKG / "build" / (LIB.stem if defines else "default")
+    objdir.mkdir(parents=True, exist_ok=True)
     objs = []
     procs = []
     for src in sources():
         obj = objdir / (src.stem + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -373,20 +373,9 @@ __device__ __forceinline__ void reduce_scatter6(const double d[6], int sub, Stor
 // trig cache: entry e < 6(k+1): layer e/6, slot e%6 (q0: theta/2, phi, lam; q1: theta/2, phi, lam)
 //             entries 6(k+1)+4g+{0,1,2,3}: gate g: phi_c, phi_g, a_c, a_g   (parameter-bound block gates)
 // ------------------------------------------------------------------------------------------------
-// Layout of a team's parameter / gradient vectors.  Entry p lives at vidx<LPP, RSTR>(p) = (p / LPP) * RSTR + p % LPP:
-//   RSTR == LPP  the plain contiguous vector (streaming kernels: rows staged per team);
-//   RSTR == 32   "lane columns" (K5): entry p belongs to lane p % LPP of the team and entries LPP apart sit one 32-wide
-//                warp row apart, so every lane-private access of a warp instruction touches 32 consecutive words whatever
-//                per-team buffer / history slot offsets are in play (offsets move whole rows) -- conflict-free.
-template <int LPP, int RSTR>
-__device__ __forceinline__ int vidx(int p) {
-  return (RSTR == LPP) ? p : (p / LPP) * RSTR + (p % LPP);
-}
-
-template <int LPP = 1, int RSTR = 1>
 __device__ __forceinline__ double slot_value(const KTemplate& kt, const double* xs, int g, int s) {
   const int p = kt.slot_param[g][s];
-  return p >= 0 ? xs[vidx<LPP, RSTR>(p)] : kt.slot_const[g][s];
+  return p >= 0 ? xs[p] : kt.slot_const[g][s];
 }
 
 // GM_SYM kernels are the hot instantiations: RZ layers (vz_only) and gate trig entries are compiled out of them
@@ -394,14 +383,13 @@ __device__ __forceinline__ double slot_value(const KTemplate& kt, const double* 
 // CANON = canonical parameter layout: the caller keeps x (and the gradient) in circuit creation order, entry 6*layer+slot,
 // every layer present, no parameter-bound gate -- no index tables are read (K5 permutes to/from the API order at the
 // problem boundaries).
-template <int LPP, int GM, bool CANON = false, int RSTR = LPP>
+template <int LPP, int GM, bool CANON = false>
 __device__ __forceinline__ void fill_trig(const KTemplate& kt, const double* xs, double2* tg, int sub) {
   if (CANON) {
     const int n1 = 6 * (kt.k + 1);
     for (int e = sub; e < n1; e += LPP) {
       double2 cs;
-      const double xe = xs[(e / LPP) * RSTR + sub];  // (e % LPP == sub: the lane's own entries)
-      const double a = (e % 3 == 0) ? 0.5 * xe : xe;
+      const double a = (e % 3 == 0) ? 0.5 * xs[e] : xs[e];
       fast_sincos(a, &cs.y, &cs.x);
       tg[e] = cs;
     }
@@ -416,8 +404,7 @@ __device__ __forceinline__ void fill_trig(const KTemplate& kt, const double* xs,
       const int p = kt.p1q[layer][s];
       if (p >= 0) {
         const bool half = vz ? true : (s == 0 || s == 3);
-        const double xp = xs[vidx<LPP, RSTR>(p)];
-        const double a = half ? 0.5 * xp : xp;
+        const double a = half ? 0.5 * xs[p] : xs[p];
         fast_sincos(a, &cs.y, &cs.x);
       }
     } else if (GM == GM_BLOCK) {
@@ -426,13 +413,13 @@ __device__ __forceinline__ void fill_trig(const KTemplate& kt, const double* xs,
       if (kt.gate_kind == SLAM_GATE_RISWAP) {
         // RiSwap(alpha) in block form: phi_c = pi (so that -i e^{-i phi_c} = +i), a_c = pi*alpha/2, a_g = 0
         if (w == 0) cs = make_double2(-1.0, 0.0);
-        if (w == 2) sincos(1.5707963267948966 * slot_value<LPP, RSTR>(kt, xs, g, 0), &cs.y, &cs.x);
+        if (w == 2) sincos(1.5707963267948966 * slot_value(kt, xs, g, 0), &cs.y, &cs.x);
       } else {  // SLAM_GATE_CG slots: phi_c, phi_g, gc, gg, t
         double a;
-        if (w == 0) a = slot_value<LPP, RSTR>(kt, xs, g, 0);
-        else if (w == 1) a = slot_value<LPP, RSTR>(kt, xs, g, 1);
-        else if (w == 2) a = slot_value<LPP, RSTR>(kt, xs, g, 2) * slot_value<LPP, RSTR>(kt, xs, g, 4);
-        else a = slot_value<LPP, RSTR>(kt, xs, g, 3) * slot_value<LPP, RSTR>(kt, xs, g, 4);
+        if (w == 0) a = slot_value(kt, xs, g, 0);
+        else if (w == 1) a = slot_value(kt, xs, g, 1);
+        else if (w == 2) a = slot_value(kt, xs, g, 2) * slot_value(kt, xs, g, 4);
+        else a = slot_value(kt, xs, g, 3) * slot_value(kt, xs, g, 4);
         sincos(a, &cs.y, &cs.x);
       }
     }
@@ -528,13 +515,13 @@ __device__ __forceinline__ void cost_from_abs(int cost_kind, double a, double& l
 //   vcol[c][a] = V[a][sub*CPL + c]  (this lane's target columns)
 // returns loss (identical on every lane of the team); *T_out = Tr(V^dag U)
 // ------------------------------------------------------------------------------------------------
-template <int LPP, int GM, bool WANT_GRAD, bool CANON = false, int RSTR = LPP>
+template <int LPP, int GM, bool WANT_GRAD, bool CANON = false>
 __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const double* xs, double2* tg, double* gs,
                                                  const cd vcol[4 / LPP][4], int cost_kind, int sub, cd* T_out) {
   constexpr int CPL = 4 / LPP;
-  fill_trig<LPP, GM, CANON, RSTR>(kt, xs, tg, sub);
+  fill_trig<LPP, GM, CANON>(kt, xs, tg, sub);
   if (WANT_GRAD && !CANON)  // (canonical layout: every entry is stored below)
-    for (int j = sub; j < kt.P; j += LPP) gs[(j / LPP) * RSTR + sub] = 0.0;
+    for (int j = sub; j < kt.P; j += LPP) gs[j] = 0.0;
   __syncwarp();
 
   cd r[CPL][4];
@@ -590,8 +577,8 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
         d0 = team_sum<LPP>(0.5 * d0);
         d3 = team_sum<LPP>(0.5 * d3);
         if (sub == 0) {
-          if (kt.p1q[i][0] >= 0) gs[vidx<LPP, RSTR>(kt.p1q[i][0])] = d0;
-          if (kt.p1q[i][3] >= 0) gs[vidx<LPP, RSTR>(kt.p1q[i][3])] = d3;
+          if (kt.p1q[i][0] >= 0) gs[kt.p1q[i][0]] = d0;
+          if (kt.p1q[i][3] >= 0) gs[kt.p1q[i][3]] = d3;
         }
       } else {
         double dq[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
@@ -609,10 +596,10 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
         }
         reduce_scatter6<LPP>(d, sub, [&](int s, double v) {
           if (CANON) {
-            gs[vidx<LPP, RSTR>(6 * i + s)] = v;
+            gs[6 * i + s] = v;
           } else {
             const int p = kt.p1q[i][s];
-            if (p >= 0) gs[vidx<LPP, RSTR>(p)] = v;
+            if (p >= 0) gs[p] = v;
           }
         });
       }
@@ -654,16 +641,15 @@ __device__ __forceinline__ double loss_grad_team(const KTemplate& kt, const doub
         if (sub == 0) {
           if (kt.gate_kind == SLAM_GATE_RISWAP) {
             const int p = kt.slot_param[g][0];
-            if (p >= 0) gs[vidx<LPP, RSTR>(p)] = 1.5707963267948966 * d_ac;
+            if (p >= 0) gs[p] = 1.5707963267948966 * d_ac;
           } else {
-            const double gc = slot_value<LPP, RSTR>(kt, xs, g, 2), gg = slot_value<LPP, RSTR>(kt, xs, g, 3),
-                         tt = slot_value<LPP, RSTR>(kt, xs, g, 4);
+            const double gc = slot_value(kt, xs, g, 2), gg = slot_value(kt, xs, g, 3), tt = slot_value(kt, xs, g, 4);
             int p;
-            if ((p = kt.slot_param[g][0]) >= 0) gs[vidx<LPP, RSTR>(p)] = d_pc;
-            if ((p = kt.slot_param[g][1]) >= 0) gs[vidx<LPP, RSTR>(p)] = d_pg;
-            if ((p = kt.slot_param[g][2]) >= 0) gs[vidx<LPP, RSTR>(p)] = tt * d_ac;
-            if ((p = kt.slot_param[g][3]) >= 0) gs[vidx<LPP, RSTR>(p)] = tt * d_ag;
-            if ((p = kt.slot_param[g][4]) >= 0) gs[vidx<LPP, RSTR>(p)] = gc * d_ac + gg * d_ag;
+            if ((p = kt.slot_param[g][0]) >= 0) gs[p] = d_pc;
+            if ((p = kt.slot_param[g][1]) >= 0) gs[p] = d_pg;
+            if ((p = kt.slot_param[g][2]) >= 0) gs[p] = tt * d_ac;
+            if ((p = kt.slot_param[g][3]) >= 0) gs[p] = tt * d_ag;
+            if ((p = kt.slot_param[g][4]) >= 0) gs[p] = gc * d_ac + gg * d_ag;
           }
         }
       }

@@ -600,6 +600,7 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   if (opts->cost_kind != SLAM_COST_BASIC && opts->cost_kind != SLAM_COST_SQUARE && opts->cost_kind != SLAM_COST_BASIC_INVERSE)
     return SLAM_ERR_UNSUPPORTED;  // the coordinate-based functionals are piecewise constant (8-dp rounding): no gradient
   if (opts->max_iter < 1 || desc->n_params < 1 || central < 0 || central > 2) return SLAM_ERR_INVALID;
+  if ((opts->lower == nullptr) != (opts->upper == nullptr)) return SLAM_ERR_INVALID;  // box = both arrays (+-inf allowed)
   if (Nt == 0) return SLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
@@ -642,8 +643,8 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   { const char* dbg = getenv("SLAM_B200_FD_DEBUG"); A.debug = (dbg && dbg[0] == '1') ? 1 : 0; }
   A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
-  A.lower = (opts->lower && opts->upper) ? opts->lower : nullptr;
-  A.upper = A.lower ? opts->upper : nullptr;
+  A.lower = opts->lower;
+  A.upper = opts->upper;
   A.con_max = opts->con_max; A.con_mu = opts->con_mu; A.con_lambda = opts->con_lambda;
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved; A.ws = ws; A.T = T;

@@ -14,8 +14,8 @@
 // j = sub + LPP i (i < NPL) and keeps its slice of the two-loop working vector in registers, so the recursion is
 // a stream of independent shared-memory loads and FMAs with one shuffle reduction per history pair.
 //
-// The kernel is instantiated per gate mode in slam_lbfgs_{sym,block,dense}.cu (parallel compilation); the C ABI
-// entry point and the launch configuration live in slam_lbfgs.cu.
+// The kernel is instantiated per gate mode in slam_lbfgs_{sym_hi32,sym,block,dense}.cu (parallel compilation); the C ABI
+// entry points and the launch configuration live in slam_lbfgs.cu.
 #pragma once
 #include <cfloat>
 
@@ -55,6 +55,7 @@ struct LbfgsArgs {
   unsigned long long* next;  // work counter
   int32_t* solved;           // per-target flag (early exit)
   const int32_t* solved_in;  // flags of the launch for the previous template size (may still be written), or null
+  unsigned long long* best_key;  // per-target packed (success class, k, loss, restart) minimum (SlamOptOpts.best_key), or null
 };
 
 // launch configuration chosen on the host (slam_lbfgs.cu)
@@ -69,15 +70,9 @@ struct LbfgsCfg {
   size_t smem;
 };
 
-// history element: float halves the dominant shared-memory consumer (the curvature scalars are computed from the
-// rounded pairs, so the two-loop recursion stays self-consistent)
-struct HistF32 {
-  typedef float T;
-  static __device__ __forceinline__ T pack(double v) { return (float)v; }
-  static __device__ __forceinline__ double unpack(T v) { return (double)v; }
-};
-// upper half of the double (sign, exponent, 20 mantissa bits): unpacking is a register move instead of an F2F
-// conversion on the quarter-rate pipe
+// history element: the upper half of the double (sign, exponent, 20 mantissa bits) halves the dominant shared-memory consumer
+// (the curvature scalars are computed from the rounded pairs, so the two-loop recursion stays self-consistent) and
+// unpacking is a register move instead of an F2F conversion on the quarter-rate pipe
 struct HistHi32 {
   typedef int T;
   static __device__ __forceinline__ T pack(double v) {
@@ -88,6 +83,25 @@ struct HistHi32 {
 };
 
 enum { ST_IDLE = 0, ST_INIT = 1, ST_LS = 2 };
+
+// Packed per-target reduction key (SlamOptOpts.best_key): a 64-bit unsigned minimum over all restarts of all chained launches
+// implements the merge rule of optimizer.py:283-303 -- the smallest template size that reached the threshold, else the lowest
+// loss seen -- with ONE fire-and-forget atomic per retired restart (no lock, nothing for the warp to wait on):
+//   bit 63      0 = loss below the success threshold, 1 = not
+//   bits 62-59  k for successes (smaller k wins), 0 otherwise
+//   bits 58-12  the top 47 bits of the (non-negative) loss: sign-less exponent + 36 mantissa bits, order preserving
+//   bits 11-8   k          bits 7-0  restart       (where the winner's row is: slam_best_gather reads it back)
+// Non-finite losses never enter the reduction.
+__host__ __device__ __forceinline__ unsigned long long best_key_pack(double f, bool success, int k, int restart) {
+#ifdef __CUDA_ARCH__
+  const unsigned long long fb = (unsigned long long)__double_as_longlong(f);
+#else
+  unsigned long long fb;
+  memcpy(&fb, &f, sizeof(fb));
+#endif
+  return (success ? 0ULL : (1ULL << 63)) | ((unsigned long long)(success ? (k & 15) : 0) << 59) | (((fb >> 16) & ((1ULL << 47) - 1)) << 12) |
+         ((unsigned long long)(k & 15) << 8) | (unsigned long long)(restart & 255);
+}
 
 // LPP  = lanes per problem; MAXT = CTA size the kernel is compiled for (register cap = 64K / MAXT);
 // NPL  = vector entries per lane held in registers (Pp <= LPP * NPL; Pp == LPP * NPL when EXACT);
@@ -182,7 +196,9 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
             double* x1 = base + 2 * Pp;
             for (int c = sub; c < P; c += LPP) {
               const int j = EXACT ? kt.p1q[c / 6][c % 6] : c;  // API index of internal entry c
-              x1[c] = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
+              double v = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
+              if (EXTRAS && A.lower) v = fmin(fmax(v, A.lower[j]), A.upper[j]);  // start inside the box
+              x1[c] = v;
             }
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
@@ -469,6 +485,8 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
         A.out_loss[pid] = f;
         A.out_iters[pid] = iter;
         if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + tgt, 1);
+        if (A.best_key && f == f && f >= 0.0 && f < DBL_MAX)
+          atomicMin(A.best_key + tgt, best_key_pack(f, f < A.success_threshold, kt.k, (int)(pid - tgt * A.restarts)));
       }
       for (int c = sub; c < P; c += LPP) A.out_x[pid * P + (EXACT ? kt.p1q[c / 6][c % 6] : c)] = xf[c];
       state = ST_IDLE;
@@ -533,9 +551,9 @@ static int dispatch_exact(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCf
 }
 
 // per-gate-mode entry points (one translation unit each)
-int lbfgs_launch_sym(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, int hist_kind, cudaStream_t st);
-int lbfgs_launch_block(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, int hist_kind, cudaStream_t st);
-int lbfgs_launch_dense(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, int hist_kind, cudaStream_t st);
+int lbfgs_launch_sym(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, cudaStream_t st);
+int lbfgs_launch_block(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, cudaStream_t st);
+int lbfgs_launch_dense(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, cudaStream_t st);
 bool lbfgs_has_exact(int lpp, int npl);
 
 }  // namespace slam

@@ -3,8 +3,7 @@
 
 namespace slam {
 
-int lbfgs_launch_block(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, int hist_kind, cudaStream_t st) {
-  (void)hist_kind;
+int lbfgs_launch_block(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, cudaStream_t st) {
   if (c.extras) return dispatch_generic<GM_BLOCK, HistHi32, true>(kt, A, c, st);
   return dispatch_generic<GM_BLOCK, HistHi32, false>(kt, A, c, st);
 }

@@ -1,13 +1,14 @@
-// K5 instantiations for constant symmetric gates (GM_SYM: RiSwap, ConversionGain with zero phases) -- the headline path;
-// (s, y) history stored as the upper half of the double (HistHi32).
+// K5 instantiations for constant symmetric gates (GM_SYM: RiSwap, ConversionGain with zero phases) -- the headline path:
+// exact-length kernels for the canonical templates P = 6(k+1).
 #include "slam_lbfgs.cuh"
 
 namespace slam {
 
-int lbfgs_launch_sym_hi32(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, cudaStream_t st) {
-  if (c.extras) return dispatch_generic<GM_SYM, HistHi32, true>(kt, A, c, st);
-  if (c.exact) return dispatch_exact<GM_SYM, HistHi32>(kt, A, c, st);
-  return dispatch_generic<GM_SYM, HistHi32, false>(kt, A, c, st);
+int lbfgs_launch_sym_generic(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, cudaStream_t st);
+
+int lbfgs_launch_sym(const KTemplate& kt, const LbfgsArgs& A, const LbfgsCfg& c, cudaStream_t st) {
+  if (c.exact && !c.extras) return dispatch_exact<GM_SYM, HistHi32>(kt, A, c, st);
+  return lbfgs_launch_sym_generic(kt, A, c, st);
 }
 
 }  // namespace slam

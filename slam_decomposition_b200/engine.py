@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import SlamNmOpts, SlamOptOpts, SlamTemplateDesc, check, load
 
 __all__ = [
-    "template_eval", "loss_grad", "weyl", "lbfgs_solve", "fd_lbfgs_solve", "nm_solve", "nm_defaults", "coverage_mc", "pd_trajectory", "fp64_peak", "opt_defaults",
+    "template_eval", "loss_grad", "weyl", "lbfgs_solve", "best_gather", "fd_lbfgs_solve", "nm_solve", "nm_defaults", "coverage_mc", "pd_trajectory", "fp64_peak", "opt_defaults",
     "require_cuda",
 ]
 
@@ -91,9 +91,17 @@ def loss_grad(desc: SlamTemplateDesc, x: torch.Tensor, V: torch.Tensor, tgt_idx:
         tgt_idx = _dev(tgt_idx, torch.int32, "tgt_idx")
         if tgt_idx.numel() != B:
             raise ValueError("tgt_idx must have B entries")
+    if out_loss is not None:
+        _dev(out_loss, torch.float64, "out_loss")
+        if out_loss.shape != (B,) or not out_loss.is_contiguous():
+            raise ValueError("loss_grad: out_loss must be a contiguous [B] tensor")
     loss = out_loss if out_loss is not None else torch.empty(B, dtype=torch.float64, device=x.device)
     grad = None
     if want_grad:
+        if out_grad is not None:
+            _dev(out_grad, torch.float64, "out_grad")
+            if out_grad.shape != (B, P) or not out_grad.is_contiguous():
+                raise ValueError("loss_grad: out_grad must be a contiguous [B,P] tensor")
         grad = out_grad if out_grad is not None else torch.empty((B, P), dtype=torch.float64, device=x.device)
     trace = torch.empty(B, dtype=torch.complex128, device=x.device) if want_trace else None
     with torch.cuda.device(x.device):
@@ -126,10 +134,23 @@ def opt_defaults() -> SlamOptOpts:
     return o
 
 
+def _check_tables(name: str, out: tuple, Nt: int, restarts: int, P: int) -> tuple:
+    """Shape / dtype / contiguity of caller-provided (loss [Nt,R], x [Nt,R,P], iters [Nt,R]) result tables: the kernels
+    write them through raw pointers."""
+    loss, x, iters = out
+    if (loss.shape != (Nt, restarts) or x.shape != (Nt, restarts, P) or iters.shape != (Nt, restarts)
+            or not (loss.is_contiguous() and x.is_contiguous() and iters.is_contiguous())):
+        raise ValueError(f"{name}: preallocated outputs have the wrong shape")
+    _dev(loss, torch.float64, "out loss"), _dev(x, torch.float64, "out x"), _dev(iters, torch.int32, "out iters")
+    return loss, x, iters
+
+
 def lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: SlamOptOpts,
                 x0: Optional[torch.Tensor] = None, seed: int = 0, active: Optional[torch.Tensor] = None,
-                evals: Optional[torch.Tensor] = None, out: Optional[tuple] = None):
-    """K5: returns (loss [Nt,R], x [Nt,R,P], iters [Nt,R]).  `out` = preallocated (loss, x, iters) to reuse."""
+                evals: Optional[torch.Tensor] = None, out: Optional[tuple] = None, best_key: Optional[torch.Tensor] = None):
+    """K5: returns (loss [Nt,R], x [Nt,R,P], iters [Nt,R]).  `out` = preallocated (loss, x, iters) to reuse.
+    `best_key` = int64 [Nt] tensor holding the packed per-target reduction keys (SlamOptOpts.best_key; initialise to -1 =
+    all ones); `best_gather` reads the winners back."""
     V = _dev(V, torch.complex128, "V")
     Nt = V.shape[0]
     P = desc.n_params
@@ -140,12 +161,17 @@ def lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: Sl
             raise ValueError(f"x0 must be [{Nt},{restarts},{P}]")
     if active is not None:
         active = _dev(active, torch.int32, "active")
+        if active.numel() != Nt:
+            raise ValueError("active must have one entry per target")
+    o = opts
+    if best_key is not None:
+        _dev(best_key, torch.int64, "best_key")
+        if best_key.shape != (Nt,) or not best_key.is_contiguous():
+            raise ValueError("lbfgs_solve: best_key must be a contiguous int64 [Nt] tensor")
+        o = SlamOptOpts.from_buffer_copy(opts)
+        o.best_key = best_key.data_ptr()
     if out is not None:
-        loss, x, iters = out
-        if (loss.shape != (Nt, restarts) or x.shape != (Nt, restarts, P) or iters.shape != (Nt, restarts)
-                or not (loss.is_contiguous() and x.is_contiguous() and iters.is_contiguous())):
-            raise ValueError("lbfgs_solve: preallocated outputs have the wrong shape")
-        _dev(loss, torch.float64, "out loss"), _dev(x, torch.float64, "out x"), _dev(iters, torch.int32, "out iters")
+        loss, x, iters = _check_tables("lbfgs_solve", out, Nt, restarts, P)
     else:
         loss = torch.empty((Nt, restarts), dtype=torch.float64, device=V.device)
         x = torch.empty((Nt, restarts, P), dtype=torch.float64, device=V.device)
@@ -157,13 +183,39 @@ def lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: Sl
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         check(lib.slam_lbfgs_solve(C.byref(desc), _ptr(V), Nt, int(restarts), _ptr(x0), ld, C.c_uint64(seed), _ptr(active),
-                                   C.byref(opts), _ptr(loss), _ptr(x), _ptr(iters), _ptr(evals), _stream()),
+                                   C.byref(o), _ptr(loss), _ptr(x), _ptr(iters), _ptr(evals), _stream()),
               "slam_lbfgs_solve")
         if ev is not None:
             ev[1].record()
             LBFGS_EVENTS.append((desc.k, ev[0], ev[1]))
     _count()
     return loss, x, iters
+
+
+def best_gather(best_key: torch.Tensor, tables, restarts: int, ldx: int):
+    """Winners of the packed per-target reduction: `tables` = [(k, loss [Nt,R], x [Nt,R,P]), ...] of the chained launches ->
+    (best_loss [Nt] f64, best_k [Nt] i32, best_P [Nt] i32, best_x [Nt, ldx] f64), one small kernel."""
+    _dev(best_key, torch.int64, "best_key")
+    Nt = best_key.shape[0]
+    n = len(tables)
+    ks = (C.c_int32 * n)(*[int(k) for k, _, _ in tables])
+    Ps = (C.c_int32 * n)(*[int(x.shape[2]) for _, _, x in tables])
+    for _, loss, x in tables:
+        _check_tables("best_gather", (loss, x, torch.empty((Nt, restarts), dtype=torch.int32, device=loss.device)), Nt, restarts,
+                      x.shape[2])
+    lp = (C.c_void_p * n)(*[loss.data_ptr() for _, loss, _ in tables])
+    xp = (C.c_void_p * n)(*[x.data_ptr() for _, _, x in tables])
+    dev = best_key.device
+    bl = torch.empty(Nt, dtype=torch.float64, device=dev)
+    bk = torch.empty(Nt, dtype=torch.int32, device=dev)
+    bp = torch.empty(Nt, dtype=torch.int32, device=dev)
+    bx = torch.empty((Nt, int(ldx)), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        lib = _enter(best_key)
+        check(lib.slam_best_gather(_ptr(best_key), Nt, int(restarts), n, ks, Ps, lp, xp, _ptr(bl), _ptr(bk), _ptr(bp), _ptr(bx),
+                                   int(ldx), _stream()), "slam_best_gather")
+    _count()
+    return bl, bk, bp, bx
 
 
 def fd_lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: SlamOptOpts,
@@ -184,10 +236,7 @@ def fd_lbfgs_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts:
     if active is not None:
         active = _dev(active, torch.int32, "active")
     if out is not None:
-        loss, x, iters = out
-        if (loss.shape != (Nt, restarts) or x.shape != (Nt, restarts, P) or iters.shape != (Nt, restarts)
-                or not (loss.is_contiguous() and x.is_contiguous() and iters.is_contiguous())):
-            raise ValueError("fd_lbfgs_solve: preallocated outputs have the wrong shape")
+        loss, x, iters = _check_tables("fd_lbfgs_solve", out, Nt, restarts, P)
     else:
         loss = torch.empty((Nt, restarts), dtype=torch.float64, device=V.device)
         x = torch.empty((Nt, restarts, P), dtype=torch.float64, device=V.device)
@@ -221,7 +270,7 @@ def nm_solve(desc: SlamTemplateDesc, V: torch.Tensor, restarts: int, opts: SlamN
     if active is not None:
         active = _dev(active, torch.int32, "active")
     if out is not None:
-        loss, x, iters = out
+        loss, x, iters = _check_tables("nm_solve", out, Nt, restarts, P)
     else:
         loss = torch.empty((Nt, restarts), dtype=torch.float64, device=V.device)
         x = torch.empty((Nt, restarts, P), dtype=torch.float64, device=V.device)
@@ -242,7 +291,11 @@ def coverage_mc(desc: SlamTemplateDesc, seed: int, first_sample: int, n_samples:
     if hist is None:
         hist = torch.zeros(nbins ** 3, dtype=torch.int64, device=device)
     else:
-        hist = _dev(hist, torch.int64, "hist")
+        if hist.dtype != torch.int64 or not hist.is_cuda:
+            raise TypeError("hist must be a CUDA int64 tensor")
+        if not hist.is_contiguous() or hist.numel() != int(nbins) ** 3:
+            # the kernel indexes hist[(b0 * nbins + b1) * nbins + b2] through a raw pointer
+            raise ValueError(f"hist must be contiguous with nbins^3 = {int(nbins) ** 3} entries, got {hist.numel()}")
     coords = torch.empty((n_samples, 3), dtype=torch.float64, device=device) if want_coords else None
     with torch.cuda.device(device):
         lib = _enter(hist)

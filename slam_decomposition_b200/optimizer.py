@@ -11,7 +11,6 @@ Return contract kept (optimizer.py:186): ``(training_loss, coordinate
 from __future__ import annotations
 
 import logging
-import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -51,9 +50,10 @@ class TemplateOptimizer:
         self.smush_adjoint = True  # K5c on parameter-bound smush templates: analytic adjoint gradient (False = differences)
         # K5 launches of consecutive template sizes are chained on two streams (SlamOptOpts.solved_in / solved_out) so the
         # next size fills the SMs the tail of the current one leaves idle and no host round trip separates them
-        self.pipeline = os.environ.get("SLAM_B200_PIPELINE", "1") != "0"
+        self.pipeline = True  # set False to run one launch per size with a host round trip in between (A/B)
         self._pipe = None  # streams + per-size workspaces of the chained sweep
         self._host_x = None  # pinned staging buffer of approximate_targets()
+        self.tune = {}  # e.g. {"tune_hist_min": 4}: SlamOptOpts.tune_* fields applied to the default options
         self.launch_evals = []  # (k, loss+grad evaluations) per slam_lbfgs_solve launch while engine.LBFGS_EVENTS is on
 
     # ------------------------------------------------------------------------------------------
@@ -79,7 +79,15 @@ class TemplateOptimizer:
         V = torch.as_tensor(np.asarray(target_u, dtype=np.complex128)[None], device=engine.require_cuda())
         res = self._run_batch(V, target_spanning_range)
         P = int(res["best_P"][0])
-        return float(res["best_loss"][0]), res["best_x"][0, :P].cpu().numpy(), int(res["best_k"][0])
+        best_k = int(res["best_k"][0])
+        if best_k > 0 and isinstance(self.basis, _CircuitTemplateBase):
+            # the reference's loop ends built at the size it breaks on (optimizer.py:297-303), so basis.eval(best_Xk) works
+            # right after _run; the batched sweep ends at max(k), hence the rebuild (gate cycles restored: not a new build
+            # in the reference's sequence)
+            state = self.basis.cycle_state()
+            self.basis.build(n_repetitions=best_k)
+            self.basis.set_cycle_state(state)
+        return float(res["best_loss"][0]), res["best_x"][0, :P].cpu().numpy(), best_k
 
     # ------------------------------------------------------------------------------------------
     # batched core
@@ -147,6 +155,8 @@ class TemplateOptimizer:
         R = int(self.training_restarts)
         if opts is None:
             opts = engine.opt_defaults()
+            for name, val in self.tune.items():  # explicit launch tuning of K5 (SlamOptOpts.tune_*), for A/B measurements
+                setattr(opts, name, int(val))
         opts.cost_kind = ck if ck in (_lib.COST_BASIC, _lib.COST_SQUARE) else _lib.COST_BASIC
         opts.success_threshold = float(self.success_threshold)
         opts.f_stop = min(opts.f_stop, 1e-3 * float(self.success_threshold))
@@ -170,7 +180,10 @@ class TemplateOptimizer:
         best_P = torch.zeros((Nt,), dtype=torch.int32, device=device)
         # the parameter table is sized for the largest template of the range up front, so that its shape does not depend
         # on where this rank's targets happen to be solved (ranks gather their tables with one fixed-shape collective)
+        state = b.cycle_state() if hasattr(b, "cycle_state") else None
         b.build(n_repetitions=max(k_list))
+        if state is not None:
+            b.set_cycle_state(state)  # (a sizing build the reference does not do: its gate cycles must not advance)
         best_x = torch.zeros((Nt, b.desc.n_params), dtype=torch.float64, device=device)
         active = torch.ones((Nt,), dtype=torch.int32, device=device)
         evals = torch.zeros(1, dtype=torch.int64, device=device)
@@ -192,11 +205,13 @@ class TemplateOptimizer:
             opts.x0_lo, opts.x0_hi = lo, hi
             bound_t = None
             if getattr(b, "using_bounds", False):
-                # box bounds in API order (basisv2.py:162-164); None = unbounded on that side.  The reference switches
-                # scipy to L-BFGS-B here (optimizer.py:257-258); the device optimiser projects onto the box.
+                # box bounds in API order (basisv2.py:162-164).  Once any bound is set, the reference's parameter_guess
+                # gives EVERY parameter a bound -- its own, or the default (-4 pi, 4 pi) (basisv2.py:156-166) -- and passes
+                # the list to scipy's L-BFGS-B (optimizer.py:257-258), so unlisted parameters are boxed too; a None side
+                # of an explicit bound is unbounded.  The device optimiser projects onto the box.
                 lo_b, hi_b = [], []
                 for prm in b.circuit.parameters:
-                    bd = b.bounds.get(prm.name, None) or (None, None)
+                    bd = b.bounds.get(prm.name, None) or b.default_bound
                     l_, h_ = bd[0], bd[1]
                     l_ = -np.inf if l_ is None else float(l_)
                     h_ = np.inf if h_ is None else float(h_)
@@ -247,7 +262,8 @@ class TemplateOptimizer:
                                                     out=(ws["loss"], x, ws["iters"]))
             if timing:
                 marks.append((k, evals.clone()))  # async snapshot; converted to per-launch deltas after the sweep
-            lmin, rmin = loss.min(dim=1)
+            # a restart whose objective went non-finite reports NaN (DBL_MAX = skipped): neither may win the reduction
+            lmin, rmin = torch.nan_to_num(loss, nan=float("inf")).min(dim=1)
             improved = (active != 0) & (lmin < best_loss)
             xsel = x[ar, rmin]
             if best_x is None or best_x.shape[1] < P:
@@ -339,24 +355,33 @@ class TemplateOptimizer:
     # chained sweep: one K5 launch per template size, alternating between two streams
     # ------------------------------------------------------------------------------------------
     def _all_lbfgs(self, k_list, ck) -> bool:
+        """Probe every size of the range for the solver it needs.  The reference builds each size once, in order, and its
+        gate cycles advance across builds (basis.py:68-72); the probing builds are undone so that the sweep's own builds see
+        the sequence the reference's k-loop sees."""
         b = self.basis
-        for k in k_list:
-            b.build(n_repetitions=k)
-            if self._solver(b.desc, ck) != "lbfgs":
-                return False
-        return True
+        state = b.cycle_state() if hasattr(b, "cycle_state") else None
+        try:
+            for k in k_list:
+                b.build(n_repetitions=k)
+                if self._solver(b.desc, ck) != "lbfgs":
+                    return False
+            return True
+        finally:
+            if state is not None:
+                b.set_cycle_state(state)
 
     def _run_chained(self, V: torch.Tensor, k_list, opts) -> dict:
-        """The k-loop of optimizer.py:233-303 without host round trips.  Every size gets its own result tables; the launch
-        for size k_{i+1} reads the (live) solved flags of size k_i and skips the targets already below the threshold, which
-        is the reference's early exit; launches alternate between two streams, so the CTAs of the next size start on the SMs
-        the draining launch frees.  The merge afterwards keeps, per target, the smallest size that succeeded (else the lowest
-        loss seen), exactly what the sequential loop keeps."""
+        """The k-loop of optimizer.py:233-303 without host round trips and without host-side merging.  Every size gets its
+        own per-restart tables; the launch for size k_{i+1} reads the (live) solved flags of size k_i and skips the targets
+        already below the threshold, which is the reference's early exit; launches alternate between two streams, so the CTAs
+        of the next size start on the SMs the draining launch frees.  Every retired restart also feeds one packed 64-bit
+        atomic minimum per target (SlamOptOpts.best_key: the smallest size that succeeded, else the lowest loss seen --
+        exactly what the sequential loop keeps), and one small kernel (slam_best_gather) copies the winners out of the
+        tables afterwards: no eager tensor ops between or after the launches."""
         b = self.basis
         device = V.device
         Nt = V.shape[0]
         R = int(self.training_restarts)
-        thr = float(self.success_threshold)
         main = torch.cuda.current_stream(device)
         descs = []
         for k in k_list:
@@ -369,14 +394,15 @@ class TemplateOptimizer:
             pipe = {"key": key, "streams": (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)),
                     "flags": torch.empty((len(descs), Nt), dtype=torch.int32, device=device),
                     "evals": torch.empty(len(descs), dtype=torch.int64, device=device),
-                    "ar": torch.arange(Nt, device=device),
+                    "best_key": torch.empty(Nt, dtype=torch.int64, device=device),
                     "tab": [{"loss": torch.empty((Nt, R), dtype=torch.float64, device=device),
                              "iters": torch.empty((Nt, R), dtype=torch.int32, device=device),
                              "x": torch.empty((Nt, R, P), dtype=torch.float64, device=device)} for _, _, P in descs]}
             self._pipe = pipe
-        flags, evals, ar = pipe["flags"], pipe["evals"], pipe["ar"]
+        flags, evals, best_key = pipe["flags"], pipe["evals"], pipe["best_key"]
         flags.zero_()
         evals.zero_()
+        best_key.fill_(-1)
         timing = engine.LBFGS_EVENTS is not None
         span = None
         if engine.LBFGS_SPANS is not None:
@@ -384,7 +410,6 @@ class TemplateOptimizer:
             span[0].record(main)
         ready = torch.cuda.Event()
         ready.record(main)
-        reduced = []
         for i, (k, desc, P) in enumerate(descs):
             logging.info(f"Starting opt on template size {k}")
             st = pipe["streams"][i % 2]
@@ -399,30 +424,15 @@ class TemplateOptimizer:
                 o.solved_in = flags[i - 1].data_ptr() if i > 0 else None
                 o.solved_out = flags[i].data_ptr()
                 seed = int(np.random.randint(0, 2 ** 62))
-                loss, x, _ = engine.lbfgs_solve(desc, V, R, o, x0=x0, seed=seed, active=None, evals=evals[i:i + 1],
-                                                out=(tab["loss"], tab["x"], tab["iters"]))
-                lmin, rmin = loss.min(dim=1)
-                reduced.append((k, P, lmin, x[ar, rmin]))
+                engine.lbfgs_solve(desc, V, R, o, x0=x0, seed=seed, active=None, evals=evals[i:i + 1],
+                                   out=(tab["loss"], tab["x"], tab["iters"]), best_key=best_key)
         for st in pipe["streams"]:
             main.wait_stream(st)
         if span is not None:
             span[1].record(main)
             engine.LBFGS_SPANS.append(span)
-        # merge (main stream): sizes ascending, a target stops taking part once it is below the threshold
-        best_loss = torch.full((Nt,), float("inf"), dtype=torch.float64, device=device)
-        best_k = torch.full((Nt,), -1, dtype=torch.int32, device=device)
-        best_P = torch.zeros((Nt,), dtype=torch.int32, device=device)
-        best_x = torch.zeros((Nt, max(Pmax, descs[-1][2])), dtype=torch.float64, device=device)
-        active = torch.ones((Nt,), dtype=torch.bool, device=device)
-        for k, P, lmin, xsel in reduced:
-            improved = active & (lmin < best_loss)
-            best_x[:, :P] = torch.where(improved[:, None], xsel, best_x[:, :P])
-            if best_x.shape[1] > P:
-                best_x[:, P:] = torch.where(improved[:, None], torch.zeros_like(best_x[:, P:]), best_x[:, P:])
-            best_loss = torch.where(improved, lmin, best_loss)
-            best_k = torch.where(improved, torch.full_like(best_k, k), best_k)
-            best_P = torch.where(improved, torch.full_like(best_P, P), best_P)
-            active = active & ~(best_loss < thr)
+        best_loss, best_k, best_P, best_x = engine.best_gather(
+            best_key, [(k, pipe["tab"][i]["loss"], pipe["tab"][i]["x"]) for i, (k, _, _) in enumerate(descs)], R, Pmax)
         ev_host = evals.cpu().numpy()
         self.last_stats = {"evals": int(ev_host.sum())}
         if timing:

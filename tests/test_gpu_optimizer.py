@@ -353,6 +353,51 @@ def test_chained_sweep_matches_the_sequential_k_loop():
         assert abs(O.cost(tmpl.eval(a["Xk"][i, : tmpl.n_params]), V[i], "basic") - a["loss"][i]) < 1e-10
 
 
+def test_packed_key_reduction_equals_the_reduction_of_the_restart_tables():
+    """SlamOptOpts.best_key + slam_best_gather: the per-target reduction K5 feeds with one atomic minimum per retired restart
+    (the merge of optimizer.py:283-303) must pick what a host-side reduction of the per-restart tables picks -- for one
+    launch (minimum over restarts; early exit off so that every restart runs) and chained over two sizes with the
+    reference's rule (the smallest size that succeeds, else the lowest loss) -- including many concurrent finishers of the
+    same target (few targets, many restarts).  The key keeps 47 bits of the loss, so restarts whose losses agree to ~1e-11
+    relative may tie: any of them is accepted."""
+    rng = np.random.default_rng(31)
+    for Nt, R in ((257, 8), (3, 64)):
+        V = torch.as_tensor(np.stack([O.haar_unitary(rng) for _ in range(Nt)]), device="cuda")
+        key = torch.full((Nt,), -1, dtype=torch.int64, device="cuda")
+        tables = []
+        ref_loss = np.full(Nt, np.inf)
+        ref_k = np.full(Nt, -1)
+        ref_x = [[np.zeros(26)] for _ in range(Nt)]
+        for k in (2, 3):
+            desc, _ = make_pair("riswap", (0.5,), k=k)
+            o = engine.opt_defaults()
+            o.early_exit = 0
+            loss, x, _ = engine.lbfgs_solve(desc, V, R, o, seed=5 + k, best_key=key)
+            tables.append((k, loss, x))
+            loss, x = loss.cpu().numpy(), x.cpu().numpy()
+            P = desc.n_params
+            for t in range(Nt):
+                f = loss[t].min()
+                ok_new, ok_old = f < 1e-10, ref_loss[t] < 1e-10
+                if (ok_new and (not ok_old or k < ref_k[t])) or (not ok_new and not ok_old and f < ref_loss[t]):
+                    ref_loss[t], ref_k[t] = f, k
+                    ties = np.nonzero(np.abs(loss[t] - f) <= 2e-11 * max(f, 1e-300))[0]
+                    ref_x[t] = [(loss[t, rr], np.concatenate([x[t, rr], np.zeros(26 - P)])) for rr in ties]
+        bl, bk, bp, bx = engine.best_gather(key, tables, R, 26)
+        bl, bk, bp, bx = bl.cpu().numpy(), bk.cpu().numpy(), bp.cpu().numpy(), bx.cpu().numpy()
+        assert np.array_equal(bk, ref_k), Nt
+        assert np.array_equal(bp, np.where(ref_k == 2, 18, 24))
+        for t in range(Nt):
+            assert any(bl[t] == fl and np.array_equal(bx[t], cand) for fl, cand in ref_x[t]), (Nt, t)
+    # a target with no result keeps the initial key and gathers as (+inf, -1, 0, zeros)
+    key = torch.full((2,), -1, dtype=torch.int64, device="cuda")
+    desc, _ = make_pair("riswap", (0.5,), k=2)
+    loss = torch.zeros((2, 4), dtype=torch.float64, device="cuda")
+    x = torch.ones((2, 4, desc.n_params), dtype=torch.float64, device="cuda")
+    bl, bk, bp, bx = engine.best_gather(key, [(2, loss, x)], 4, desc.n_params)
+    assert torch.isinf(bl).all() and (bk == -1).all() and (bp == 0).all() and (bx == 0).all()
+
+
 def test_cost_constrained_template_against_scipy_slsqp():
     """CircuitTemplateV2.set_constraint (basisv2.py:192-203): circuit_cost(x) = sum of the RiSwap alphas <= budget.  The
     reference switches scipy to SLSQP (optimizer.py:259-264); the device path is an augmented Lagrangian around K5c.

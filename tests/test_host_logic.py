@@ -153,3 +153,42 @@ def test_circuit_cost_batch_matches_the_per_sample_shim():
     assert np.isclose(b2.constraint_func["fun"](X[0]), 1.5 - b2.circuit_cost(X[0]))
     b2.remove_constraint()
     assert not b2.using_constraints
+
+
+def test_hull_coverage_reproduces_the_reference_base_volume_of_two_sqrt_iswaps():
+    """Post-processing of a coverage histogram (parallel_drive_volume.py:343-396), on the host: a cloud that fills the
+    known span of two sqrt(iSWAP) gates, {c1 >= c2 + c3} inside the half-chamber, must give the Haar fraction the
+    reference recorded as its base volume (data/extended_results.json: sqiSwap k=2 -> 0.7901173636843226), contain CNOT
+    and B but not SWAP -- and a flat cloud (the c3 = 0 plane of two CNOTs) has zero volume."""
+    import json
+    import os
+
+    from slam_decomposition_b200.utils.gates import parallel_drive_volume as pdv
+
+    ref = 0.7901173636843226
+    pts, w = pdv.half_chamber_grid(256)
+    sel = pts[:, 0] >= pts[:, 1] + pts[:, 2]
+    assert abs((w * sel).sum() / w.sum() - ref) < 2e-4  # the Haar density and the grid quadrature themselves
+    # (a) exact sample points: a dense cloud in the span (the hull of samples is an inner approximation)
+    rng = np.random.default_rng(0)
+    cloud = pts[sel][rng.choice(int(sel.sum()), 200_000, replace=False)]
+    out = pdv.hull_coverage(cloud, plain_cloud=cloud, grid=128)
+    assert abs(out["extended_vol"] - ref) < 5e-3 and abs(out["base_vol"] - ref) < 5e-3
+    assert (out["has_CNOT"], out["has_SWAP"], out["has_B"]) == (True, False, True)
+    # (b) a histogram of the same cloud: voxel approximation, good to a voxel's worth of volume
+    nb = 128
+    hist = np.bincount(np.ravel_multi_index(np.floor(cloud * 2 * nb).astype(int).T, (nb, nb, nb)), minlength=nb ** 3)
+    out = pdv.hull_coverage(hist, nbins=nb, grid=128)
+    assert abs(out["extended_vol"] - ref) < 0.02 and out["base_vol"] == 0.0
+    # (c) a flat cloud (the c3 = 0 plane that two CNOTs span) has zero volume and contains nothing by itself
+    flat = cloud.copy()
+    flat[:, 2] = 0.0
+    out = pdv.hull_coverage(flat, grid=64)
+    assert out["extended_vol"] == 0.0 and out["base_vol"] == 0.0
+    assert (out["has_CNOT"], out["has_SWAP"], out["has_B"]) == (False, False, False)
+    # with exact base flags (base_reachable) the base set decides
+    out = pdv.hull_coverage(flat, grid=64, base_flags={"CNOT": True, "SWAP": False, "B": True})
+    assert (out["has_CNOT"], out["has_SWAP"], out["has_B"]) == (True, False, True)
+    # the reference's recorded table is shipped as a golden fixture for the GPU-side comparison
+    tab = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "extended_results.json")))
+    assert tab["sqiSwap"]["2"][0] == ref

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.slam_abi_version() == 3
+    assert lib.slam_abi_version() == 4
     assert lib.slam_status_string(0) == b"ok"
     assert b"invalid" in lib.slam_status_string(-1)
     assert b"unsupported" in lib.slam_status_string(-2)
@@ -44,7 +44,8 @@ def test_struct_layouts_match_the_header():
     # SlamTemplateDesc: 8 int32 + int32[9][6] + int32[8][40] + double[8][40] + double[32]
     assert ctypes.sizeof(_lib.SlamTemplateDesc) == 32 + 9 * 6 * 4 + 8 * 40 * 4 + 8 * 40 * 8 + 32 * 8
     assert _lib.SlamTemplateDesc.slot_const.offset % 8 == 0
-    assert ctypes.sizeof(_lib.SlamOptOpts) == 4 * 4 + 7 * 8 + 2 * 4 + 9 * 8
+    # 4 int32, 7 double, 2 int32, 9 pointers/doubles (v3), then v4: best_key pointer + 4 int32 (tune_*)
+    assert ctypes.sizeof(_lib.SlamOptOpts) == 4 * 4 + 7 * 8 + 2 * 4 + 9 * 8 + 8 + 4 * 4
 
 
 def test_opt_defaults_follow_the_reference_constants(lib):
@@ -188,6 +189,19 @@ def test_optimiser_option_validation_needs_no_device(lib):
     o = opts()
     o.cost_kind = _lib.COST_MAKHLIN_FUNCTIONAL
     assert fd(o, 0) == -2   # coordinate-based functionals have no gradient (8-dp rounding)
+    # ABI v4: the packed per-target key holds 8 bits of restart index; box bounds come as a pair; tuning values are checked
+    o = opts()
+    o.best_key = 8
+    assert lib.slam_lbfgs_solve(ctypes.byref(desc), fake, 4, 257, None, desc.n_params, 0, None, ctypes.byref(o), fake, fake,
+                                fake, None, None) == -2
+    o = opts()
+    o.lower = 8  # without upper
+    assert lbfgs(o) == -1
+    assert fd(o, 1) == -1
+    o = opts()
+    o.tune_lanes = 3
+    assert lbfgs(o) == -1
+    assert lib.slam_best_gather(None, 4, 2, 1, None, None, None, None, None, None, None, None, 4, None) == -1
     sdesc, _ = make_pair("smush", ("Q", "Q", np.pi / 2, 0.0, "Q", "Q", "Q", "Q", 0.5), k=1, T=2, no_exterior_1q=True)
     o = opts()
     o.con_mu = 1.0
