@@ -14,7 +14,9 @@
  *     (e.g. torch.Tensor.data_ptr()); the library never frees or retains it.
  *   - `desc` pointers are HOST pointers to a POD descriptor, read during the call only.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
- *     asynchronous on that stream unless stated otherwise, re-entrant, and keep no global state.
+ *     asynchronous on that stream unless stated otherwise and re-entrant.  The only state the library keeps is one private,
+ *     lazily created cudaMemPool_t per device for stream-ordered scratch (work counters, optimiser workspaces; at most 1 GiB
+ *     of freed blocks is retained, larger workspaces return to the driver); the device's default pool is not touched.
  *   - complex128 values are (re, im) pairs of doubles; 4x4 matrices are row-major, 32 doubles.
  *   - return value: 0 = ok, negative = SlamStatus error (no exception crosses the ABI).
  *   - parameter vectors (`x`, `grad`) are in the reference's API order: the order of
@@ -124,6 +126,11 @@ int slam_template_eval(const SlamTemplateDesc* desc, const double* x, int64_t ld
 int slam_loss_grad(const SlamTemplateDesc* desc, const double* x, int64_t ldx, const double* V, int64_t Nt,
                    const int32_t* tgt_idx, int32_t cost_kind, double* loss, double* grad, int64_t ldg,
                    double* trace, int64_t B, void* stream);
+/* as slam_loss_grad with an explicit team width: lanes per row, 1, 2 or 4 (0 = automatic: 2 up to k = 4, 4 beyond);
+   ignored for templates with parameter-bound smush gates (one thread per row) */
+int slam_loss_grad_lanes(const SlamTemplateDesc* desc, const double* x, int64_t ldx, const double* V, int64_t Nt,
+                         const int32_t* tgt_idx, int32_t cost_kind, double* loss, double* grad, int64_t ldg,
+                         double* trace, int64_t B, int32_t lanes, void* stream);
 
 /*
  * K3  Weyl-chamber coordinates and Makhlin invariants of a batch of 4x4 unitaries.

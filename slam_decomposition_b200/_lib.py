@@ -99,6 +99,8 @@ _PROTOS = {
     "slam_template_eval": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, _P, C.c_int64, _P]),
     "slam_loss_grad": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, _P, C.c_int64, _P, C.c_int32, _P, _P,
                                  C.c_int64, _P, C.c_int64, _P]),
+    "slam_loss_grad_lanes": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, _P, C.c_int64, _P, C.c_int32, _P, _P,
+                                       C.c_int64, _P, C.c_int64, C.c_int32, _P]),
     "slam_weyl": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int32, _P]),
     "slam_opt_defaults": (None, [C.POINTER(SlamOptOpts)]),
     "slam_lbfgs_solve": (C.c_int, [C.POINTER(SlamTemplateDesc), _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_uint64, _P,

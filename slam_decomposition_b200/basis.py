@@ -122,7 +122,7 @@ class HamiltonianTemplate(VariationalTemplate):
         """Nothing to extend (optimizer.py:240-248 only builds circuit templates).  For the scalar-argument
         conversion/gain Hamiltonians the template is lowered to a one-gate descriptor whose parameters H0, H1, ... are
         construct_U's positional arguments, so the device optimisers can run it."""
-        from .hamiltonian import ConversionGainHamiltonian, ConversionGainPhaseHamiltonian, SnailEffectiveHamiltonian
+        from .hamiltonian import ConversionGainHamiltonian, ConversionGainPhaseHamiltonian
         from .utils.gates.custom_gates import ConversionGainGate
 
         h = self.h if isinstance(self.h, type) else type(self.h)
@@ -132,8 +132,6 @@ class HamiltonianTemplate(VariationalTemplate):
             gate = ConversionGainGate(ps[0], ps[1], ps[2], ps[3], ps[4])  # positional quirk kept
         elif issubclass(h, ConversionGainHamiltonian):
             gate = ConversionGainGate(0.0, 0.0, ps[0], ps[1], 1.0)
-        elif issubclass(h, SnailEffectiveHamiltonian):
-            gate = ConversionGainGate(0.0, 0.0, ps[0], 0.0, 1.0)
         else:
             raise NotImplementedError(f"{h.__name__}: vector-argument Hamiltonians cannot be driven by a flat Xk "
                                       "(construct_U(*Xk) fails in the reference as well)")

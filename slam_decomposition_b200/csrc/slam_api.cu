@@ -1,4 +1,6 @@
 // slam_api.cu -- housekeeping entry points and descriptor lowering for libslam_b200.so
+#include <mutex>
+
 #include "slam_host.h"
 
 namespace slam {
@@ -9,11 +11,25 @@ void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
-int keep_async_pool(int device) {
-  cudaMemPool_t pool;
-  SLAM_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
-  unsigned long long keep = ~0ULL;
-  SLAM_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+int scratch_pool(int device, cudaMemPool_t* pool) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  static bool made[64] = {};
+  if (device < 0 || device >= 64) return SLAM_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!made[device]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    SLAM_CUDA_CHECK(cudaMemPoolCreate(&pools[device], &props));
+    unsigned long long keep = 1ULL << 30;
+    SLAM_CUDA_CHECK(cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep));
+    made[device] = true;
+  }
+  *pool = pools[device];
   return SLAM_OK;
 }
 

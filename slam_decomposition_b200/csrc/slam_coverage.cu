@@ -114,34 +114,19 @@ extern "C" int slam_coverage_mc(const SlamTemplateDesc* desc, uint64_t seed, int
   // 128-thread units per SM the kernels are compiled for (register cap 255 / 168 / 128).  Measured on B200, Msamples/s at
   // 2 / 3 / 4 units: sqrt(iSWAP) k=3 plain 2355 / 2771 / 2928, CNOT k=3 plain 2338 / 2745 / 2903 (latency bound: 16 warps/SM
   // win despite 160 B of spills); sqrt(iSWAP) k=3 smush, phase-locked, 542 / 542 / 515 (scripts/cov_ab.py).
-  const char* e = getenv("SLAM_B200_COV_MINB");
-  const int minb = e ? atoi(e) : 0;
   // Phase-locked variant (one CTA per SM, barriers at the layer / gate / slice boundaries): on for the smush templates,
   // whose kernel is 75 KB of code (sqrt(iSWAP) k=3 smush 458 -> 542, CNOT k=2 smush 424 -> 454 Msamples/s); off for the
   // closed-form gates, whose hot code fits the 32 KB instruction cache (2928 vs 2862 Msamples/s).
-  const char* es = getenv("SLAM_B200_COV_SYNC");
-  const bool sync = es ? atoi(es) != 0 : kt.gmode == GM_SMUSH;
+  const bool sync = kt.gmode == GM_SMUSH;
 #define SLAM_COV(GM, MB)                                                                                                  \
   return (sync && (size_t)kt.P * 128 * MB * sizeof(double) <= 200 * 1024)                                                  \
              ? launch_coverage<GM, MB, true>(kt, seed, first_sample, n_samples, lo, span, nbins, hist, coords, sms, st)   \
              : launch_coverage<GM, MB, false>(kt, seed, first_sample, n_samples, lo, span, nbins, hist, coords, sms, st)
-  switch (kt.gmode) {
-    case GM_SYM:
-      if (minb == 2) SLAM_COV(GM_SYM, 2);
-      if (minb == 3) SLAM_COV(GM_SYM, 3);
-      SLAM_COV(GM_SYM, 4);
-    case GM_BLOCK:
-      if (minb == 2) SLAM_COV(GM_BLOCK, 2);
-      if (minb == 3) SLAM_COV(GM_BLOCK, 3);
-      SLAM_COV(GM_BLOCK, 4);
-    case GM_DENSE:
-      if (minb == 2) SLAM_COV(GM_DENSE, 2);
-      if (minb == 3) SLAM_COV(GM_DENSE, 3);
-      SLAM_COV(GM_DENSE, 4);
-    default:
-      if (minb == 3) SLAM_COV(GM_SMUSH, 3);
-      if (minb == 4) SLAM_COV(GM_SMUSH, 4);
-      SLAM_COV(GM_SMUSH, 2);
+  switch (kt.gmode) {  // closed-form gates: 4 units (16 warps/SM); smush: 2 units (255 registers)
+    case GM_SYM: SLAM_COV(GM_SYM, 4);
+    case GM_BLOCK: SLAM_COV(GM_BLOCK, 4);
+    case GM_DENSE: SLAM_COV(GM_DENSE, 4);
+    default: SLAM_COV(GM_SMUSH, 2);
   }
 #undef SLAM_COV
   return SLAM_OK;

@@ -120,12 +120,8 @@ static int pick_threads(const KTemplate& kt, int lpp, bool grad) {
 
 // lanes per problem for the streaming kernels: measured on B200 (scripts/quick_bench.py, loss+grad, % of DFMA peak)
 //   k=1: LPP 4/2/1 = 55/62/57 %   k=3: 71/79/65 %   k=6: 79/70/46 %   -> 2 lanes up to k=4, 4 lanes beyond
-static int pick_lpp(const KTemplate& kt) {
-  const char* e = getenv("SLAM_B200_LPP");
-  if (e) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) return v;
-  }
+static int pick_lpp(const KTemplate& kt, int lanes) {
+  if (lanes == 1 || lanes == 2 || lanes == 4) return lanes;
   return kt.k <= 4 ? 2 : 4;
 }
 
@@ -210,7 +206,14 @@ extern "C" int slam_template_eval(const SlamTemplateDesc* desc, const double* x,
 extern "C" int slam_loss_grad(const SlamTemplateDesc* desc, const double* x, int64_t ldx, const double* V, int64_t Nt,
                               const int32_t* tgt_idx, int32_t cost_kind, double* loss, double* grad, int64_t ldg,
                               double* trace, int64_t B, void* stream) {
+  return slam_loss_grad_lanes(desc, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, 0, stream);
+}
+
+extern "C" int slam_loss_grad_lanes(const SlamTemplateDesc* desc, const double* x, int64_t ldx, const double* V, int64_t Nt,
+                                    const int32_t* tgt_idx, int32_t cost_kind, double* loss, double* grad, int64_t ldg,
+                                    double* trace, int64_t B, int32_t lanes, void* stream) {
   if (!desc || B < 0 || ldx < desc->n_params) return SLAM_ERR_INVALID;
+  if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4) return SLAM_ERR_INVALID;
   if (grad && ldg < desc->n_params) return SLAM_ERR_INVALID;
   if (cost_kind < SLAM_COST_BASIC || cost_kind > SLAM_COST_BASIC_INVERSE) return SLAM_ERR_INVALID;  // optimizer.py:211
   if (B == 0) return SLAM_OK;  // empty batch: nothing to read or write
@@ -225,7 +228,7 @@ extern "C" int slam_loss_grad(const SlamTemplateDesc* desc, const double* x, int
     rc = lower_const_smush(desc, &kt, st);
     if (rc != SLAM_OK) return rc;
   }
-  switch (pick_lpp(kt)) {
+  switch (pick_lpp(kt, lanes)) {
     case 1: return dispatch_loss_grad<1>(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, st);
     case 2: return dispatch_loss_grad<2>(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, st);
     default: return dispatch_loss_grad<4>(kt, x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, st);

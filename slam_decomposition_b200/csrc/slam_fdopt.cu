@@ -616,31 +616,29 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   int dev = 0, sms = 0;
   SLAM_CUDA_CHECK(cudaGetDevice(&dev));
   SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  rc = keep_async_pool(dev);
-  if (rc != SLAM_OK) return rc;
   const int n = kt.P;
   const int64_t total = Nt * (int64_t)restarts;
   const int threads = central == 2 ? kAdjCta : 128;
   int64_t blocks = std::min<int64_t>((int64_t)sms * (256 / threads), (total + threads - 1) / threads);
   // (5 + 2 m) double vectors per thread (the adjoint mode keeps its direction in thread-local memory and uses 4 + 2 m)
   const size_t per_thread = (size_t)(5 + 2 * kFdHist) * n * sizeof(double);
+  while (blocks > 1 && per_thread * threads * (size_t)blocks > ((size_t)4 << 30)) blocks /= 2;  // workspace <= 4 GiB
   const int64_t T = blocks * threads;
 
+  Scratch scratch(st);
   unsigned long long* next = nullptr;
   int32_t* solved = nullptr;
   double* ws = nullptr;
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&next, sizeof(unsigned long long), st));
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&solved, sizeof(int32_t) * (size_t)Nt, st));
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&ws, per_thread * (size_t)T, st));
-  SLAM_CUDA_CHECK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
-  SLAM_CUDA_CHECK(cudaMemsetAsync(solved, 0, sizeof(int32_t) * (size_t)Nt, st));
+  if ((rc = scratch.alloc(&next, sizeof(unsigned long long), true)) != SLAM_OK) return rc;
+  if ((rc = scratch.alloc(&solved, sizeof(int32_t) * (size_t)Nt, true)) != SLAM_OK) return rc;
+  if ((rc = scratch.alloc(&ws, per_thread * (size_t)T)) != SLAM_OK) return rc;
 
   FdArgs A;
   A.V = V; A.x0 = x0; A.ldx0 = ldx0; A.seed = seed; A.active = active; A.Nt = Nt; A.restarts = restarts;
   A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit; A.central = central;
   // smush gates carry no circuit_fidelity factor, so 1 - BasicCostInverse x 1 is BasicCost (optimizer.py:200-201)
   if (central == 2 && A.cost_kind == SLAM_COST_BASIC_INVERSE) A.cost_kind = SLAM_COST_BASIC;
-  { const char* dbg = getenv("SLAM_B200_FD_DEBUG"); A.debug = (dbg && dbg[0] == '1') ? 1 : 0; }
+  A.debug = 0;
   A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
   A.lower = opts->lower;
@@ -656,9 +654,6 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   else if (central == 1) fd_lbfgs_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
   else fd_lbfgs_kernel<0><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
   cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(next, st);
-  cudaFreeAsync(solved, st);
-  cudaFreeAsync(ws, st);
   if (e != cudaSuccess) {
     set_cuda_error(e, "fd_lbfgs_kernel launch");
     return SLAM_ERR_CUDA;

@@ -154,30 +154,11 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
   if (smem > (size_t)max_smem) return SLAM_ERR_UNSUPPORTED;
 
   // stream-ordered scratch: work counter + per-target early-exit flags
-  rc = keep_async_pool(dev);
-  if (rc != SLAM_OK) return rc;
+  Scratch scratch(st);
   unsigned long long* next = nullptr;
-  int32_t* solved = nullptr;
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&next, sizeof(unsigned long long), st));
-  auto cleanup = [&]() {  // (also the error paths: nothing allocated here outlives the call)
-    cudaFreeAsync(next, st);
-    if (solved && !opts->solved_out) cudaFreeAsync(solved, st);
-  };
-  cudaError_t e = cudaMemsetAsync(next, 0, sizeof(unsigned long long), st);
-  if (e == cudaSuccess) {
-    if (opts->solved_out) {
-      solved = opts->solved_out;  // caller-owned (and caller-zeroed) flags of a chained launch
-    } else {
-      e = cudaMallocAsync((void**)&solved, sizeof(int32_t) * (size_t)Nt, st);
-      if (e != cudaSuccess) solved = nullptr;
-      else e = cudaMemsetAsync(solved, 0, sizeof(int32_t) * (size_t)Nt, st);
-    }
-  }
-  if (e != cudaSuccess) {
-    cleanup();
-    set_cuda_error(e, "K5 scratch (work counter / solved flags)");
-    return SLAM_ERR_CUDA;
-  }
+  int32_t* solved = opts->solved_out;  // caller-owned (and caller-zeroed) flags of a chained launch, else scratch
+  if ((rc = scratch.alloc(&next, sizeof(unsigned long long), true)) != SLAM_OK) return rc;
+  if (!solved && (rc = scratch.alloc(&solved, sizeof(int32_t) * (size_t)Nt, true)) != SLAM_OK) return rc;
 
   LbfgsArgs A;
   A.V = V; A.x0 = x0; A.ldx0 = ldx0; A.seed = seed; A.active = active; A.Nt = Nt; A.restarts = restarts;
@@ -201,7 +182,6 @@ extern "C" int slam_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, i
     case GM_DENSE: rc = lbfgs_launch_dense(kt, A, cfg, st); break;
     default: rc = SLAM_ERR_UNSUPPORTED;
   }
-  cleanup();
   return rc;
 }
 

@@ -217,8 +217,6 @@ extern "C" int slam_nm_solve(const SlamTemplateDesc* desc, const double* V, int6
   int dev = 0, sms = 0;
   SLAM_CUDA_CHECK(cudaGetDevice(&dev));
   SLAM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  rc = keep_async_pool(dev);
-  if (rc != SLAM_OK) return rc;
   const int n = kt.P;
   const int64_t total = Nt * (int64_t)restarts;
   const int threads = 128;
@@ -227,14 +225,13 @@ extern "C" int slam_nm_solve(const SlamTemplateDesc* desc, const double* V, int6
   while (blocks > 1 && per_thread * threads * (size_t)blocks > ((size_t)4 << 30)) blocks /= 2;  // workspace <= 4 GiB
   const int64_t T = blocks * threads;
 
+  Scratch scratch(st);
   unsigned long long* next = nullptr;
   int32_t* solved = nullptr;
   double* ws = nullptr;
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&next, sizeof(unsigned long long), st));
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&solved, sizeof(int32_t) * (size_t)Nt, st));
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&ws, per_thread * (size_t)T, st));
-  SLAM_CUDA_CHECK(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
-  SLAM_CUDA_CHECK(cudaMemsetAsync(solved, 0, sizeof(int32_t) * (size_t)Nt, st));
+  if ((rc = scratch.alloc(&next, sizeof(unsigned long long), true)) != SLAM_OK) return rc;
+  if ((rc = scratch.alloc(&solved, sizeof(int32_t) * (size_t)Nt, true)) != SLAM_OK) return rc;
+  if ((rc = scratch.alloc(&ws, per_thread * (size_t)T)) != SLAM_OK) return rc;
 
   NmArgs A;
   A.V = V; A.x0 = x0; A.ldx0 = ldx0; A.seed = seed; A.active = active; A.Nt = Nt; A.restarts = restarts;
@@ -245,9 +242,6 @@ extern "C" int slam_nm_solve(const SlamTemplateDesc* desc, const double* V, int6
   A.next = next; A.solved = solved; A.ws = ws; A.T = T;
   nm_kernel<<<(unsigned)blocks, threads, 0, st>>>(A, kt);
   cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(next, st);
-  cudaFreeAsync(solved, st);
-  cudaFreeAsync(ws, st);
   if (e != cudaSuccess) {
     set_cuda_error(e, "nm_kernel launch");
     return SLAM_ERR_CUDA;

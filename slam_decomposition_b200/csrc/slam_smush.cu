@@ -113,16 +113,13 @@ int lower_const_smush(const SlamTemplateDesc* d, KTemplate* kt, cudaStream_t st)
   (void)d;
   KTemplate tmp = *kt;
   tmp.gmode = GM_SMUSH;
-  int device = 0;
-  SLAM_CUDA_CHECK(cudaGetDevice(&device));
-  if (int rc = keep_async_pool(device)) return rc;
+  Scratch scratch(st);
   double* dev = nullptr;
-  SLAM_CUDA_CHECK(cudaMallocAsync((void**)&dev, sizeof(double) * 32 * SLAM_MAX_K, st));
+  if (int rc = scratch.alloc(&dev, sizeof(double) * 32 * SLAM_MAX_K)) return rc;
   const_smush_kernel<<<1, SLAM_MAX_K, 0, st>>>(dev, tmp);
   SLAM_CUDA_CHECK(cudaGetLastError());
   SLAM_CUDA_CHECK(cudaMemcpyAsync(kt->dense, dev, sizeof(double) * 32 * kt->k, cudaMemcpyDeviceToHost, st));
   SLAM_CUDA_CHECK(cudaStreamSynchronize(st));
-  SLAM_CUDA_CHECK(cudaFreeAsync(dev, st));
   kt->gmode = GM_DENSE;
   return SLAM_OK;
 }
@@ -201,13 +198,9 @@ extern "C" int slam_pd_trajectory(const double* gate, const double* gx, const do
   using namespace slam;
   if (!gate || !gx || !gy || N < 1 || R < 1 || B < 0 || (!coords && !Ufinal)) return SLAM_ERR_INVALID;
   if (B == 0) return SLAM_OK;
-  const char* e = getenv("SLAM_B200_TRAJ_SYNC");
-  if (e ? atoi(e) != 0 : true) {
+  {  // phase-locked CTA (barriers at the slice boundaries): 2.08 vs 1.75 G trajectory points/s without them
     const unsigned grid = (unsigned)((B + 255) / 256);
     trajectory_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(gate, gx, gy, N, R, dt, flags, coords, Ufinal, B);
-  } else {
-    const unsigned grid = (unsigned)((B + 127) / 128);
-    trajectory_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(gate, gx, gy, N, R, dt, flags, coords, Ufinal, B);
   }
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;

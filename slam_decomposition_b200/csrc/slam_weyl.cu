@@ -46,10 +46,8 @@ extern "C" int slam_weyl(const double* U, int64_t B, double* c, double* g, int32
   if (!U || B < 0 || (!c && !g)) return SLAM_ERR_INVALID;
   if (B == 0) return SLAM_OK;
   const unsigned grid = (unsigned)((B + 127) / 128);
-  const char* e = getenv("SLAM_B200_WEYL_MINB");
   // 16 warps/SM (128 registers, 144 B of spills) beat 12 warps (168 registers, none): 2045 vs 1861 Mmatrices/s on B200
-  if (e && atoi(e) == 3) weyl_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(U, B, c, g, flags);
-  else weyl_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(U, B, c, g, flags);
+  weyl_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(U, B, c, g, flags);
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
 }

@@ -52,19 +52,32 @@ def allreduce_histogram(hist: torch.Tensor) -> torch.Tensor:
     return hist
 
 
-def allgather_table(table: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """Concatenate per-rank result tables along dim 0 (every tensor must have the same dim-0 length on all
-    ranks: shards are equal-sized in the weak-scaling sweep; ragged shards are padded by the caller)."""
+def allgather_table(table: Dict[str, torch.Tensor], async_op: bool = False, pad_to: int | None = None):
+    """Concatenate per-rank result tables along dim 0.  Every tensor must have the same dim-0 length on all ranks (equal
+    shards in the weak-scaling sweep); ragged shards pass `pad_to` = the largest shard length and get zero-padded rows.
+    With `async_op` the collectives are only issued: returns (tables, handles) and the caller calls `wait_all(handles)` before
+    it reads the tables (the gather then overlaps whatever is enqueued next)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return table
+        return (table, []) if async_op else table
     out = {}
+    handles = []
     ws = dist.get_world_size()
     for key, t in table.items():
         t = t.contiguous()
+        if pad_to is not None and t.shape[0] < pad_to:
+            pad = torch.zeros((pad_to - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            t = torch.cat([t, pad])
         full = torch.empty((ws * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(full, t)
+        h = dist.all_gather_into_tensor(full, t, async_op=async_op)
+        if async_op:
+            handles.append(h)
         out[key] = full
-    return out
+    return (out, handles) if async_op else out
+
+
+def wait_all(handles) -> None:
+    for h in handles:
+        h.wait()
 
 
 def barrier():

@@ -78,8 +78,8 @@ def template_eval(desc: SlamTemplateDesc, x: torch.Tensor) -> torch.Tensor:
 
 def loss_grad(desc: SlamTemplateDesc, x: torch.Tensor, V: torch.Tensor, tgt_idx: Optional[torch.Tensor] = None,
               cost_kind: int = 0, want_grad: bool = True, want_trace: bool = False,
-              out_loss: Optional[torch.Tensor] = None, out_grad: Optional[torch.Tensor] = None):
-    """K2: (loss [B], grad [B,P] | None, trace [B] complex | None)."""
+              out_loss: Optional[torch.Tensor] = None, out_grad: Optional[torch.Tensor] = None, lanes: int = 0):
+    """K2: (loss [B], grad [B,P] | None, trace [B] complex | None).  `lanes`: team width 1 / 2 / 4 (0 = automatic)."""
     x = _dev(x, torch.float64, "x")
     V = _dev(V, torch.complex128, "V")
     if x.dim() != 2 or x.shape[1] != desc.n_params:
@@ -106,8 +106,9 @@ def loss_grad(desc: SlamTemplateDesc, x: torch.Tensor, V: torch.Tensor, tgt_idx:
     trace = torch.empty(B, dtype=torch.complex128, device=x.device) if want_trace else None
     with torch.cuda.device(x.device):
         lib = _enter(x)
-        check(lib.slam_loss_grad(C.byref(desc), _ptr(x), max(x.stride(0), P), _ptr(V), V.shape[0], _ptr(tgt_idx),
-                                 int(cost_kind), _ptr(loss), _ptr(grad), P, _ptr(trace), B, _stream()), "slam_loss_grad")
+        check(lib.slam_loss_grad_lanes(C.byref(desc), _ptr(x), max(x.stride(0), P), _ptr(V), V.shape[0], _ptr(tgt_idx),
+                                       int(cost_kind), _ptr(loss), _ptr(grad), P, _ptr(trace), B, int(lanes), _stream()),
+              "slam_loss_grad")
     _count()
     return loss, grad, trace
 

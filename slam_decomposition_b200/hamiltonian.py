@@ -43,14 +43,6 @@ class ConversionGainHamiltonian(Hamiltonian):
         return _gate_matrix(ConversionGainGate(0.0, 0.0, float(gc), float(gg), 1.0))
 
 
-class SnailEffectiveHamiltonian(Hamiltonian):
-    @staticmethod
-    def construct_U(geff):
-        from .utils.gates.custom_gates import ConversionGainGate
-
-        return _gate_matrix(ConversionGainGate(0.0, 0.0, float(geff), 0.0, 1.0))
-
-
 class ConversionGainSmush(Hamiltonian):
     @staticmethod
     def construct_U(phi_c, phi_g, gc, gg, gxvector, gyvector, t=1):

@@ -239,7 +239,7 @@ def hull_coverage(smush_cloud, plain_cloud=None, nbins: int = 128, grid: int = 2
     return out
 
 
-def base_reachable(gc: float, gg: float, t: float, k: int, restarts: int = 16, threshold: float = 1e-10) -> dict:
+def base_reachable(gc: float, gg: float, t: float, k: int, restarts: int = 32, threshold: float = 1e-8) -> dict:
     """Exact form of `circuit_polytope.has_element(target)` for the base polytope (parallel_drive_volume.py:381-396): is
     CNOT / SWAP / B reachable by k plain basis gates with free 1Q gates?  Decided by decomposing the three gates onto the
     plain template at this k on the device (loss <= threshold)."""
@@ -256,7 +256,7 @@ def base_reachable(gc: float, gg: float, t: float, k: int, restarts: int = 16, t
     return {name: bool(res["success"][i]) for i, name in enumerate(("CNOT", "SWAP", "B"))}
 
 
-def coverage_study(gc: float, gg: float, t: float, k: int, n_samples: int = N, seed: int = 0, n_base: int = 200_000,
+def coverage_study(gc: float, gg: float, t: float, k: int, n_samples: int = N, seed: int = 0, n_base: int = 2_000_000,
                    grid: int = 128, exact_flags: bool = True) -> list:
     """One (gate, k) row of the reference's study (parallel_drive_volume.py:140-410) in its own protocol:
     `n_samples` random instances of the parallel-drive template (reference: N = 3000) -> folded cloud -> hull; base set =

@@ -39,6 +39,14 @@ def _worker(rank, world, port, n, q):
     tab = {"loss": torch.full((rows,), float(rank), dtype=torch.float64), "k": torch.full((rows,), rank + 1, dtype=torch.int32),
            "x": torch.arange(rows * 3, dtype=torch.float64).reshape(rows, 3) + 1000 * rank}
     full = D.allgather_table(tab)
+    # asynchronous form (bench.py overlaps the gather with the next sweep) and ragged shards padded to a common length
+    full_async, handles = D.allgather_table(tab, async_op=True)
+    D.wait_all(handles)
+    assert all(torch.equal(full_async[k], full[k]) for k in tab)
+    ragged = {"loss": torch.full((rows - rank,), float(rank), dtype=torch.float64)}
+    padded = D.allgather_table(ragged, pad_to=rows)
+    assert padded["loss"].shape == (w * rows,) and padded["loss"][rows - 1] == 0.0 and padded["loss"][rows] == 1.0
+    assert padded["loss"][2 * rows - 1] == 0.0  # rank 1 contributed rows - 1 rows: its last row is padding
     t = D.max_over_ranks(float(rank + 1), device="cpu")
     s = D.sum_over_ranks(float(rank + 1), device="cpu")
     D.barrier()

@@ -64,7 +64,7 @@ def test_b1_golden_vector_on_device():
 @pytest.mark.parametrize("kind,slots,kw", CASES)
 @pytest.mark.parametrize("k", [1, 3, 6])
 @pytest.mark.parametrize("cost_kind", [0, 1, 2])
-def test_loss_and_gradient_match_oracle(kind, slots, kw, k, cost_kind, monkeypatch):
+def test_loss_and_gradient_match_oracle(kind, slots, kw, k, cost_kind):
     if kw.get("no_exterior_1q") and k == 1:
         pytest.skip("no parameters")
     desc, orc = make_pair(kind, slots, k=k, **kw)
@@ -75,9 +75,8 @@ def test_loss_and_gradient_match_oracle(kind, slots, kw, k, cost_kind, monkeypat
     tgt = rng.integers(0, Nt, B).astype(np.int32)
     name = ("basic", "square", "basic_inverse")[cost_kind]
     ref = [O.loss_and_grad(orc, X[b], V[tgt[b]], name) for b in range(B)]
-    for lpp in ("4", "2", "1"):
-        monkeypatch.setenv("SLAM_B200_LPP", lpp)
-        loss, grad, trace = engine.loss_grad(desc, _dev(X), _dev(V), _dev(tgt), cost_kind=cost_kind, want_trace=True)
+    for lpp in (4, 2, 1, 0):  # every team width, and the automatic choice
+        loss, grad, trace = engine.loss_grad(desc, _dev(X), _dev(V), _dev(tgt), cost_kind=cost_kind, want_trace=True, lanes=lpp)
         loss, grad, trace = loss.cpu().numpy(), grad.cpu().numpy(), trace.cpu().numpy()
         for b in range(B):
             assert abs(loss[b] - ref[b][0]) < 1e-13
@@ -85,7 +84,7 @@ def test_loss_and_gradient_match_oracle(kind, slots, kw, k, cost_kind, monkeypat
             # gate-parameter derivatives in the oracle are central differences of the gate matrix (O(h^2))
             assert np.abs(grad[b] - ref[b][1]).max() < (1e-8 if "Q" in slots else 1e-12), (lpp, b)
         # loss-only path agrees bit-for-bit with the loss of the gradient path
-        loss2, _, _ = engine.loss_grad(desc, _dev(X), _dev(V), _dev(tgt), cost_kind=cost_kind, want_grad=False)
+        loss2, _, _ = engine.loss_grad(desc, _dev(X), _dev(V), _dev(tgt), cost_kind=cost_kind, want_grad=False, lanes=lpp)
         assert np.array_equal(loss2.cpu().numpy(), loss)
 
 
