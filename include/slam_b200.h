@@ -33,7 +33,7 @@ extern "C" {
 #endif
 
 #define SLAM_ABI_VERSION 4
-#define SLAM_MAX_K 8      /* max 2Q-gate applications per template (reference uses <= 6)       */
+#define SLAM_MAX_K 16     /* max 2Q-gate applications per template (k <= 6 in the sweeps; 15 pulse slices) */
 #define SLAM_MAX_SLOTS 40 /* max scalar slots of one 2Q gate (smush1q: 8 + 2T + 1, T <= 15)    */
 #define SLAM_MAX_PARAMS 256
 
@@ -308,6 +308,11 @@ int slam_coverage_mc(const SlamTemplateDesc* desc, uint64_t seed, int64_t first_
  */
 int slam_pd_trajectory(const double* gate, const double* gx, const double* gy, int32_t N, int32_t R, double dt,
                        int32_t flags, double* coords, double* Ufinal, int64_t B, void* stream);
+/* Multi-segment pulses: as slam_pd_trajectory with one gate row PER SLICE, gate [dev] double[B, N, 8] -- the drive phases
+   and couplings may change from slice to slice.  Replaces the composed widgets `pdgw + pdgw2 (+ pdgw3)` of
+   ParallelDrivenGateWidget.__add__ (pd_playground.py:46-58) as used by scripts/parallel_drive_swap cells 6-13.          */
+int slam_pd_trajectory_slices(const double* gate, const double* gx, const double* gy, int32_t N, int32_t R, double dt,
+                              int32_t flags, double* coords, double* Ufinal, int64_t B, void* stream);
 
 /*
  * Diagnostic: register-resident DFMA loop; writes achieved FP64 FLOP/s of the current device to

@@ -34,7 +34,7 @@ __all__ = [
     "c1c2c3", "c1c2c3_raw", "fold_c1", "g1g2g3", "g1g2g3_raw", "J_T_LI", "haar_unitary", "haar_sample_unitary",
     "loss_and_grad", "fd_gradient", "literal_objective", "literal_run", "LiteralResult",
     "philox4x32_10", "philox_uniform", "coverage_params", "coverage_points", "coverage_histogram",
-    "bin_index", "near_bin_edge", "trajectory", "F_eval", "F_lossgrad",
+    "bin_index", "near_bin_edge", "trajectory", "trajectory_segments", "F_eval", "F_lossgrad",
 ]
 
 # --------------------------------------------------------------------------------------
@@ -745,6 +745,29 @@ def trajectory(phases, gc, gg, gz1, gz2, gx_vec, gy_vec, dt: float, R: int = 5):
                 c[0] = -1 * c[0] + 1
             coords[end - 1, r] = c
         prefix = U  # last t == dt
+    return coords, U
+
+
+def trajectory_segments(gate_rows, gx_vec, gy_vec, dt: float, R: int = 5):
+    """Composed widgets ``pdgw + pdgw2 (+ ...)`` (``ParallelDrivenGateWidget.__add__``, pd_playground.py:46-58: the circuits
+    of the operands are concatenated, so every slice keeps the phases / couplings of the widget it came from) followed by
+    ``iterate_time`` (pd_playground.py:179-208).  ``gate_rows`` [N, 8] = (phase_a, phase_b, phase_c, phase_g, gc, gg, gz1,
+    gz2) per slice.  Returns (coords [N,R,3] folded & rounded, final unitary)."""
+    gate_rows = np.asarray(gate_rows, float)
+    N = len(gx_vec)
+    coords = np.zeros((N, R, 3))
+    prefix = np.eye(4, dtype=np.complex128)
+    U = prefix
+    for end in range(1, N + 1):
+        g = gate_rows[end - 1]
+        for r, t in enumerate(np.linspace(0, dt, R)):
+            Ui = smush_1qphase(g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], [gx_vec[end - 1]], [gy_vec[end - 1]], t)
+            U = Ui @ prefix
+            c = list(c1c2c3(U))
+            if c[0] > 0.5:
+                c[0] = -1 * c[0] + 1
+            coords[end - 1, r] = c
+        prefix = U
     return coords, U
 
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-SLAM_MAX_K = 8
+SLAM_MAX_K = 16
 SLAM_MAX_SLOTS = 40
 SLAM_MAX_PARAMS = 256
 
@@ -114,6 +114,7 @@ _PROTOS = {
     "slam_coverage_mc": (C.c_int, [C.POINTER(SlamTemplateDesc), C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_double,
                                    C.c_int32, _P, _P, _P]),
     "slam_pd_trajectory": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, _P, C.c_int64, _P]),
+    "slam_pd_trajectory_slices": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, _P, C.c_int64, _P]),
     "slam_fp64_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "slam_selftest_sincos": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }

@@ -44,7 +44,7 @@ static int expected_slots(int kind, int T) {
   }
 }
 
-int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_smush) {
+int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_smush, bool allow_ties) {
   if (!d || !kt) return SLAM_ERR_INVALID;
   if (d->k < 1 || d->k > SLAM_MAX_K) return SLAM_ERR_INVALID;  // basis.py:127-128 raises ValueError for k <= 0
   if (d->n_params < 0 || d->n_params > SLAM_MAX_PARAMS) return SLAM_ERR_INVALID;
@@ -81,7 +81,7 @@ int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_
     any_bound |= bound;
   }
   kt->n_trig = 6 * (d->k + 1);
-  {  // each Xk entry may be bound to at most one slot (qiskit Parameters are created once per slot, basis.py:136-169);
+  if (!allow_ties) {  // each Xk entry may be bound to at most one slot (qiskit Parameters are created once per slot, basis.py:136-169);
      // the gradient kernels store, rather than accumulate, each partial derivative
     unsigned char used[SLAM_MAX_PARAMS] = {0};
     for (int i = 0; i <= d->k; ++i)

@@ -101,7 +101,7 @@ extern "C" int slam_coverage_mc(const SlamTemplateDesc* desc, uint64_t seed, int
   if (n_samples == 0) return SLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
-  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true);
+  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true, /*allow_ties=*/true);
   if (rc != SLAM_OK) return rc;
   if (kt.gmode == GM_DENSE && desc->gate_kind != SLAM_GATE_FIXED) {
     rc = lower_const_smush(desc, &kt, st);

@@ -188,7 +188,7 @@ extern "C" int slam_template_eval(const SlamTemplateDesc* desc, const double* x,
   if (!U || (desc->n_params > 0 && !x)) return SLAM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
-  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true);
+  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true, /*allow_ties=*/true);
   if (rc != SLAM_OK) return rc;
   if (kt.gmode == GM_SMUSH) return smush_eval_launch(kt, x, ldx, U, B, st);
   if (kt.gmode == GM_DENSE && desc->gate_kind != SLAM_GATE_FIXED) {

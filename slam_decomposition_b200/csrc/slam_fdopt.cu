@@ -604,7 +604,7 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   if (Nt == 0) return SLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
-  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true);
+  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true, /*allow_ties=*/central != 2);
   if (rc != SLAM_OK) return rc;
   if (central == 2 && kt.gmode != GM_SMUSH) return SLAM_ERR_UNSUPPORTED;  // closed-form gates: slam_lbfgs_solve
   if (central == 2 && opts->con_mu != 0.0) return SLAM_ERR_UNSUPPORTED;   // the constraint term is differenced, not adjoint

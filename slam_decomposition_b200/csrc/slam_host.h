@@ -22,8 +22,11 @@ void set_cuda_error(cudaError_t e, const char* where);
   } while (0)
 
 // Validate a SlamTemplateDesc and lower it to the kernel-side KTemplate.
-//   allow_bound_smush: parameter-bound smush gates are accepted (forward-only kernels)
-int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_smush);
+//   allow_bound_smush: parameter-bound smush gates are accepted (forward evaluators and the slice adjoint)
+//   allow_ties: one Xk entry may be bound to several slots (tied pulse parameters, pd_playground / parallel_drive_swap);
+//               only for entry points that never STORE a per-slot partial derivative (forward evaluation, Nelder-Mead,
+//               finite differences, coverage)
+int compile_template(const SlamTemplateDesc* d, KTemplate* kt, bool allow_bound_smush, bool allow_ties = false);
 
 // Host evaluation of a *constant* smush gate is not done on the CPU: callers lower constant smush
 // gates to GM_DENSE by running the device smush kernel once (see slam_smush.cu).

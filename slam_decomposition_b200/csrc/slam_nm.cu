@@ -208,7 +208,7 @@ extern "C" int slam_nm_solve(const SlamTemplateDesc* desc, const double* V, int6
   if (Nt == 0) return SLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   KTemplate kt;
-  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true);
+  int rc = compile_template(desc, &kt, /*allow_bound_smush=*/true, /*allow_ties=*/true);
   if (rc != SLAM_OK) return rc;
   if (kt.gmode == GM_DENSE && desc->gate_kind != SLAM_GATE_FIXED) {
     rc = lower_const_smush(desc, &kt, st);

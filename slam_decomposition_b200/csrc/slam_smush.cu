@@ -129,14 +129,17 @@ int lower_const_smush(const SlamTemplateDesc* d, KTemplate* kt, cudaStream_t st)
 // run the same N x R loop, padding lanes recompute the last trajectory) -- see fwd1_gate in slam_fwd1.cuh
 template <bool SYNC>
 __global__ void __launch_bounds__(SYNC ? 256 : 128, SYNC ? 1 : 2)
-trajectory_kernel(const double* __restrict__ gate, const double* __restrict__ gx, const double* __restrict__ gy, int N, int Rn,
-                  double dt, int flags, double* __restrict__ coords, double* __restrict__ Ufinal, int64_t B) {
+trajectory_kernel(const double* __restrict__ gate, int gate_slice_stride, const double* __restrict__ gx,
+                  const double* __restrict__ gy, int N, int Rn, double dt, int flags, double* __restrict__ coords,
+                  double* __restrict__ Ufinal, int64_t B) {
+  // gate rows: one per trajectory (gate_slice_stride = 0) or one per SLICE (8: multi-segment pulses, whose drive phases /
+  // couplings change between segments -- ParallelDrivenGateWidget.__add__, pd_playground.py:46-58)
   const int64_t b0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = b0 < B;
   if (!SYNC && !valid) return;
   const int64_t b = valid ? b0 : B - 1;
-  const double* gp = gate + b * 8;
-  const SmushGate G = smush_gate(gp[0], gp[1], gp[2], gp[3], gp[4], gp[5], gp[6], gp[7]);
+  const double* gp = gate + b * (gate_slice_stride ? (int64_t)gate_slice_stride * N : 8);
+  SmushGate G = smush_gate(gp[0], gp[1], gp[2], gp[3], gp[4], gp[5], gp[6], gp[7]);
   cd P[4][4];  // prefix product of the completed slices, [col][row]
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -144,6 +147,10 @@ trajectory_kernel(const double* __restrict__ gate, const double* __restrict__ gx
     for (int r = 0; r < 4; ++r) P[c][r] = mkc(c == r ? 1.0 : 0.0, 0.0);
   for (int s = 0; s < N; ++s) {
     const double ax = gx[b * N + s], ay = gy[b * N + s];
+    if (gate_slice_stride && s > 0) {
+      const double* gs = gp + (int64_t)s * gate_slice_stride;
+      G = smush_gate(gs[0], gs[1], gs[2], gs[3], gs[4], gs[5], gs[6], gs[7]);
+    }
     for (int q = 0; q < Rn; ++q) {
       // np.linspace(0, dt, R)[q]; the last point is exactly dt
       const double t = (Rn == 1) ? 0.0 : ((q == Rn - 1) ? dt : dt * ((double)q / (double)(Rn - 1)));
@@ -193,15 +200,26 @@ trajectory_kernel(const double* __restrict__ gate, const double* __restrict__ gx
 
 }  // namespace slam
 
-extern "C" int slam_pd_trajectory(const double* gate, const double* gx, const double* gy, int32_t N, int32_t R, double dt,
-                                  int32_t flags, double* coords, double* Ufinal, int64_t B, void* stream) {
+static int launch_trajectory(const double* gate, int gate_slice_stride, const double* gx, const double* gy, int32_t N, int32_t R,
+                             double dt, int32_t flags, double* coords, double* Ufinal, int64_t B, void* stream) {
   using namespace slam;
   if (!gate || !gx || !gy || N < 1 || R < 1 || B < 0 || (!coords && !Ufinal)) return SLAM_ERR_INVALID;
   if (B == 0) return SLAM_OK;
   {  // phase-locked CTA (barriers at the slice boundaries): 2.08 vs 1.75 G trajectory points/s without them
     const unsigned grid = (unsigned)((B + 255) / 256);
-    trajectory_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(gate, gx, gy, N, R, dt, flags, coords, Ufinal, B);
+    trajectory_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(gate, gate_slice_stride, gx, gy, N, R, dt, flags, coords,
+                                                                     Ufinal, B);
   }
   SLAM_CUDA_CHECK(cudaGetLastError());
   return SLAM_OK;
+}
+
+extern "C" int slam_pd_trajectory(const double* gate, const double* gx, const double* gy, int32_t N, int32_t R, double dt,
+                                  int32_t flags, double* coords, double* Ufinal, int64_t B, void* stream) {
+  return launch_trajectory(gate, 0, gx, gy, N, R, dt, flags, coords, Ufinal, B, stream);
+}
+
+extern "C" int slam_pd_trajectory_slices(const double* gate, const double* gx, const double* gy, int32_t N, int32_t R, double dt,
+                                         int32_t flags, double* coords, double* Ufinal, int64_t B, void* stream) {
+  return launch_trajectory(gate, 8, gx, gy, N, R, dt, flags, coords, Ufinal, B, stream);
 }

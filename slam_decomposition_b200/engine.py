@@ -308,20 +308,23 @@ def coverage_mc(desc: SlamTemplateDesc, seed: int, first_sample: int, n_samples:
 
 def pd_trajectory(gate: torch.Tensor, gx: torch.Tensor, gy: torch.Tensor, dt: float, R: int = 5, fold: bool = True,
                   round8: bool = True, want_coords: bool = True, want_final: bool = True):
-    """K4b: gate [B,8], gx/gy [B,N] -> (coords [B,N,R,3] | None, Ufinal [B,4,4] | None)."""
+    """K4b: gate [B,8] (one gate row per trajectory) or [B,N,8] (one per slice: multi-segment pulses), gx/gy [B,N] ->
+    (coords [B,N,R,3] | None, Ufinal [B,4,4] | None)."""
     gate = _dev(gate, torch.float64, "gate")
     gx = _dev(gx, torch.float64, "gx")
     gy = _dev(gy, torch.float64, "gy")
     B, N = gx.shape
-    if gate.shape != (B, 8) or gy.shape != (B, N):
-        raise ValueError("gate must be [B,8], gx/gy [B,N]")
+    per_slice = gate.dim() == 3
+    if gate.shape != ((B, N, 8) if per_slice else (B, 8)) or gy.shape != (B, N):
+        raise ValueError("gate must be [B,8] or [B,N,8], gx/gy [B,N]")
     coords = torch.empty((B, N, R, 3), dtype=torch.float64, device=gx.device) if want_coords else None
     Uf = torch.empty((B, 4, 4), dtype=torch.complex128, device=gx.device) if want_final else None
     flags = (_lib.WEYL_FOLD if fold else 0) | (_lib.WEYL_ROUND8 if round8 else 0)
     with torch.cuda.device(gx.device):
         lib = _enter(gx)
-        check(lib.slam_pd_trajectory(_ptr(gate), _ptr(gx), _ptr(gy), N, R, float(dt), flags, _ptr(coords), _ptr(Uf), B,
-                                     _stream()), "slam_pd_trajectory")
+        fn = lib.slam_pd_trajectory_slices if per_slice else lib.slam_pd_trajectory
+        check(fn(_ptr(gate), _ptr(gx), _ptr(gy), N, R, float(dt), flags, _ptr(coords), _ptr(Uf), B, _stream()),
+              "slam_pd_trajectory")
     _count()
     return coords, Uf
 

@@ -41,8 +41,8 @@ def test_abi_version_and_status_strings(lib):
 
 
 def test_struct_layouts_match_the_header():
-    # SlamTemplateDesc: 8 int32 + int32[9][6] + int32[8][40] + double[8][40] + double[32]
-    assert ctypes.sizeof(_lib.SlamTemplateDesc) == 32 + 9 * 6 * 4 + 8 * 40 * 4 + 8 * 40 * 8 + 32 * 8
+    # SlamTemplateDesc: 8 int32 + int32[K+1][6] + int32[K][40] + double[K][40] + double[32], K = SLAM_MAX_K = 16
+    assert ctypes.sizeof(_lib.SlamTemplateDesc) == 32 + 17 * 6 * 4 + 16 * 40 * 4 + 16 * 40 * 8 + 32 * 8
     assert _lib.SlamTemplateDesc.slot_const.offset % 8 == 0
     # 4 int32, 7 double, 2 int32, 9 pointers/doubles (v3), then v4: best_key pointer + 4 int32 (tune_*)
     assert ctypes.sizeof(_lib.SlamOptOpts) == 4 * 4 + 7 * 8 + 2 * 4 + 9 * 8 + 8 + 4 * 4
