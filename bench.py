@@ -739,10 +739,12 @@ def micro_benchmarks(engine, peak_flops):
     out["smush_k3_adjoint_vs_fd_gradient"] = (out["smush_k3_loss_grad_adjoint"]["evals_per_s"] * (basis.desc.n_params + 1)
                                               / out["smush_k3_loss_only"]["evals_per_s"])
     # K5c: batched L-BFGS with the adjoint gradient on a parameter-bound smush template (sqrt(iSWAP) k=2, T=2, P=18;
-    # 16384 template-instance targets x 8 restarts from the reference's U(-4pi, 4pi) start box)
+    # 131072 template-instance targets x 8 restarts from the reference's U(-4pi, 4pi) start box: enough problems per thread
+    # (28) that the drain of the persistent grid -- restarts that run to maxiter = 2500 -- does not dominate the launch)
     b2 = pdv.smush_template(math.pi / 2, 0.0, 0.5, 2)
     rng = np.random.default_rng(3)
-    Vt = engine.template_eval(b2.desc, torch.as_tensor(rng.uniform(-1.5, 1.5, (16384, b2.desc.n_params)), device=dev))
+    n_k5c = 131072
+    Vt = engine.template_eval(b2.desc, torch.as_tensor(rng.uniform(-1.5, 1.5, (n_k5c, b2.desc.n_params)), device=dev))
     o = engine.opt_defaults()
     o.f_far = 1e-4
     o.x0_lo, o.x0_hi = -4 * math.pi, 4 * math.pi
@@ -754,7 +756,7 @@ def micro_benchmarks(engine, peak_flops):
 
     t = _timed(k5c, reps=1, warm=1)
     out["k5c_smush_adjoint_lbfgs"] = {"loss_grad_evals_per_s": int(ev.item()) / t, "ms": 1e3 * t, "params": b2.desc.n_params,
-                                      "problems": 16384 * 8}
+                                      "problems": n_k5c * 8}
     return out
 
 

@@ -587,6 +587,329 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
   if (A.out_evals && evals) atomicAdd(A.out_evals, evals);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// K5c, adjoint mode, REGISTER form (P <= 32): the same tick-structured optimiser with the bookkeeping written like K5's.
+//   * the vector length bound NQ is a compile-time constant and every vector loop is fully unrolled with a `j < n` guard, so
+//     the working vector of the two-loop recursion lives in REGISTERS and every pass issues all of its loads before the
+//     first use.  The local-array form above walks its vectors with a runtime bound: 4 loads in flight per thread, each an
+//     L2 / DRAM round trip of the interleaved workspace -- ncu: long_scoreboard 3.25 per issue, FP64 pipe 26 %
+//     (profiles/r01_k5c_adjoint_kernel_ncu_full.txt) -- and, the CTA being phase-locked, that latency is not hidden by the
+//     other warps' evaluations;
+//   * nothing vector-sized is carried across the evaluation: the search direction is recovered as (xt - x) / alpha while a
+//     line search is in progress (as K5 does), so no thread-local arrays exist at all.
+// (x, g) double-buffered and the (s, y) history stay in the interleaved global workspace (entry j of thread t at [j T + t]:
+// every access of a warp is one coalesced line).
+// ------------------------------------------------------------------------------------------------------------------
+template <int NQ>
+__global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_constant__ FdArgs A,
+                                                                   const __grid_constant__ KTemplate kt) {
+  const int n = kt.P;
+  constexpr int m = kAdjHist;
+  const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t T = A.T;
+  double* ws = A.ws + tidg;
+  auto vecp = [&](int v) -> double* { return ws + (int64_t)v * n * T; };  // entry j at [j * T]
+  auto hs = [&](int slot) -> double* { return ws + (int64_t)(4 + slot) * n * T; };
+  auto hy = [&](int slot) -> double* { return ws + (int64_t)(4 + m + slot) * n * T; };
+  const int64_t total = A.Nt * (int64_t)A.restarts;
+  const bool bounded = A.lower != nullptr;
+
+  int state = AST_IDLE, cur = 0, iter = 0, hcount = 0, hpos = 0, ls = 0;
+  bool exhausted = false, slow = false;
+  int64_t pid = 0, t = 0;
+  double f = 0.0, alpha = 1.0, gd = 0.0, gamma = 1.0, f_chk = 0.0;
+  double rho[kAdjHist];
+  unsigned long long evals = 0;
+  for (int v = 0; v < 4; ++v) {
+    double* p = vecp(v);
+    for (int j = 0; j < n; ++j) p[j * T] = 0.0;  // idle lanes evaluate their (finite) trial buffer
+  }
+
+  while (true) {
+    // ---------------- fetch -------------------------------------------------------------------------------
+    while (state == AST_IDLE && !exhausted) {
+      const unsigned long long w = atomicAdd(A.next, 1ULL);
+      if ((int64_t)w >= total) {
+        exhausted = true;
+        break;
+      }
+      const int64_t r_idx = (int64_t)w / A.Nt;
+      t = (int64_t)w - r_idx * A.Nt;
+      pid = t * A.restarts + r_idx;
+      bool skip = A.active && A.active[t] == 0;
+      if (!skip && A.early_exit) skip = *((volatile int32_t*)(A.solved + t)) != 0;
+      if (skip) {
+        A.out_loss[pid] = DBL_MAX;
+        A.out_iters[pid] = 0;
+        for (int j = 0; j < n; ++j) A.out_x[pid * n + j] = 0.0;
+        continue;
+      }
+      cur = 0;  // trial buffer = vectors (2, 3)
+      double* x1 = vecp(2);
+      for (int j = 0; j < n; ++j) {
+        double x = A.x0 ? A.x0[pid * A.ldx0 + j] : philox_param(A.seed, (uint64_t)pid, j, A.x0_lo, A.x0_span);
+        if (bounded) x = fmin(fmax(x, A.lower[j]), A.upper[j]);
+        x1[j * T] = x;
+      }
+      state = AST_INIT;
+      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false;
+    }
+    if (__syncthreads_and(state == AST_IDLE)) break;  // CTA-wide vote = the tick barrier (phase lock, see above)
+
+    // ---------------- one loss + gradient evaluation per thread (CTA-convergent) ----------------------------
+    double* xt = vecp(2 * (cur ^ 1));
+    double* gt = xt + (int64_t)n * T;
+    for (int j = 0; j < n; ++j) gt[j * T] = 0.0;
+    const double ft = adj1_nl_sync(&kt, xt, T, A.V + t * 32, A.cost_kind, gt, T);
+    if (state == AST_IDLE) continue;
+    ++evals;
+
+    // ---------------- bookkeeping (registers; every pass loads first, then computes) -------------------------
+    const double* x = vecp(2 * cur);
+    const double* g = x + (int64_t)n * T;
+    const bool first = state == AST_INIT;
+    bool done = false;
+    int reason = 0;
+    // (register budget: at most three NQ-vectors are live at any point -- the evaluation behind the call keeps 255)
+    auto load_row = [&](const double* p, double* v) {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) v[j] = (j < n) ? p[j * T] : 0.0;
+    };
+    auto project = [&](double* gp, const double* xv) {  // drop gradient components pushing against an active bound
+      if (bounded) {
+#pragma unroll
+        for (int j = 0; j < NQ; ++j)
+          if (j < n && ((xv[j] <= A.lower[j] && gp[j] > 0.0) || (xv[j] >= A.upper[j] && gp[j] < 0.0))) gp[j] = 0.0;
+      }
+    };
+    if (first || ft <= f + kArmijoFd * alpha * gd) {
+      // ---- accept ----
+      double q[NQ];  // projected gradient at the accepted point, then the two-loop working vector
+      double gmax = 0.0, gg = 0.0, sy = 0.0, yy = 0.0;
+      {
+        double a[NQ], b[NQ];
+        if (!first) {
+          load_row(xt, a);
+          load_row(x, b);
+          double* sn = hs(hpos);
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) {
+            a[j] -= b[j];  // s
+            if (j < n) sn[j * T] = a[j];
+          }
+        }
+        load_row(gt, q);
+        if (!first) {
+          load_row(g, b);
+          double* yn = hy(hpos);
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) {
+            const double yv = q[j] - b[j];
+            if (j < n) yn[j * T] = yv;
+            sy = fma(a[j], yv, sy);
+            yy = fma(yv, yv, yy);
+          }
+        }
+        if (bounded) {
+          load_row(xt, b);
+          project(q, b);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        gmax = fmax(gmax, fabs(q[j]));
+        gg = fma(q[j], q[j], gg);
+      }
+      if (!first) {
+        if (sy > 1e-14 * yy && yy > 0.0) {  // cautious update
+          rho[hpos] = 1.0 / sy;
+          gamma = sy / yy;
+          hpos = (hpos + 1 == m) ? 0 : hpos + 1;
+          hcount = min(hcount + 1, m);
+        } else if (hcount == m) {
+          hcount = m - 1;
+        }
+        ++iter;
+      } else {
+        f_chk = ft;
+      }
+      cur ^= 1;  // the trial point becomes the current point
+      f = ft;
+      if (!first && (iter & 31) == 0) {  // progress checkpoint (same rule as the local-array form)
+        slow = f > 0.97 * f_chk;
+        f_chk = f;
+      }
+      if (f < A.f_stop) reason = 1;
+      else if (gmax < A.gtol) reason = 2;
+      else if (gmax < A.gtol_far && (f > A.f_far || slow)) reason = 3;
+      else if (iter >= A.max_iter) reason = 4;
+      else if (!(f == f)) reason = 5;
+      else if (A.early_exit && (iter & 3) == 0 && *((volatile int32_t*)(A.solved + t)) != 0) reason = 6;
+      done = reason != 0;
+      if (!done) {
+        // two-loop recursion on the register vector: per pair one fully unrolled load pass for s and one for y
+        double alp[kAdjHist];
+        for (int hh = 0; hh < hcount; ++hh) {
+          int slot = hpos - 1 - hh;
+          if (slot < 0) slot += m;
+          double v[NQ];
+          load_row(hs(slot), v);
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < NQ; j += 2) {
+            a0 = fma(v[j], q[j], a0);
+            if (j + 1 < NQ) a1 = fma(v[j + 1], q[j + 1], a1);
+          }
+          const double a = (a0 + a1) * rho[slot];
+          alp[slot] = a;
+          load_row(hy(slot), v);
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) q[j] = fma(-a, v[j], q[j]);
+        }
+        if (hcount > 0) {
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) q[j] *= gamma;
+        }
+        for (int hh = hcount - 1; hh >= 0; --hh) {
+          int slot = hpos - 1 - hh;
+          if (slot < 0) slot += m;
+          double v[NQ];
+          load_row(hy(slot), v);
+          double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < NQ; j += 2) {
+            b0 = fma(v[j], q[j], b0);
+            if (j + 1 < NQ) b1 = fma(v[j + 1], q[j + 1], b1);
+          }
+          const double c = alp[slot] - (b0 + b1) * rho[slot];
+          load_row(hs(slot), v);
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) q[j] = fma(c, v[j], q[j]);
+        }
+        // d = -q ; g.d with the projected gradient (equals g.d on the free variables)
+        double xa[NQ], ga[NQ];
+        load_row(xt, xa);
+        load_row(gt, ga);
+        project(ga, xa);
+        double gdn = 0.0;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          q[j] = -q[j];
+          gdn = fma(ga[j], q[j], gdn);
+        }
+        alpha = 1.0;
+        if (hcount == 0 || !(gdn < 0.0)) {  // first step or not a descent direction: steepest descent, unit length
+          hcount = 0;
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) q[j] = -ga[j];
+          alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+        }
+        ls = 0;
+        state = AST_LS;
+        // next trial point xt + alpha d (clamped to the box) into the other buffer; directional derivative along the
+        // (projected) segment per unit alpha, as the Armijo test and the cubic use it
+        load_row(gt, ga);  // (un-projected)
+        double* xn = vecp(2 * (cur ^ 1));
+        double g_step = 0.0;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j)
+          if (j < n) {
+            double v = fma(alpha, q[j], xa[j]);
+            if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+            xn[j * T] = v;
+            g_step = fma(ga[j], v - xa[j], g_step);
+          }
+        gd = g_step / alpha;
+        if (!(gd < 0.0)) {  // zero (projected) gradient along the step
+          done = true;
+          reason = 7;
+        }
+      }
+    } else {
+      // ---- reject: backtrack along d = (xt - x) / alpha; cubic through (0, f, gd) and (alpha, ft, g_t.d) ----
+      double xv[NQ], dx[NQ];
+      load_row(x, xv);
+      load_row(xt, dx);
+      {
+        double gv[NQ];
+        load_row(gt, gv);
+        double gdt = 0.0;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          dx[j] -= xv[j];
+          gdt = fma(gv[j], dx[j], gdt);
+        }
+        gdt /= alpha;
+        double an = 0.5 * alpha;
+        if (ft == ft && gdt == gdt) {
+          const double d1 = gd + gdt - 3.0 * (ft - f) / alpha;
+          const double disc = d1 * d1 - gd * gdt;
+          if (disc >= 0.0) {
+            const double d2 = sqrt(disc);
+            const double den = gdt - gd + 2.0 * d2;
+            if (den != 0.0) {
+              const double cand = alpha - alpha * (gdt + d2 - d1) / den;
+              if (cand == cand) an = cand;
+            }
+          }
+        }
+        an = fmin(fmax(an, 0.1 * alpha), 0.5 * alpha);
+        const double ratio = an / alpha;
+        bool restart_sd = false;
+        if (++ls > 30) {
+          if (hcount > 0) {  // curvature model is bad: restart from steepest descent at the current point
+            hcount = 0;
+            restart_sd = true;
+            ls = 0;
+          } else {
+            done = true;  // no progress possible at working precision
+            reason = 8;
+          }
+        }
+        if (!done && restart_sd) {
+          load_row(g, gv);
+          project(gv, xv);
+          double gg = 0.0, g_step = 0.0;
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) gg = fma(gv[j], gv[j], gg);
+          an = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+          load_row(g, dx);  // (un-projected, for the directional derivative)
+#pragma unroll
+          for (int j = 0; j < NQ; ++j)
+            if (j < n) {
+              double v = fma(-an, gv[j], xv[j]);
+              if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+              xt[j * T] = v;
+              g_step = fma(dx[j], v - xv[j], g_step);
+            }
+          alpha = an;
+          gd = g_step / alpha;
+          if (!(gd < 0.0)) {
+            done = true;
+            reason = 7;
+          }
+        } else if (!done) {
+          // the segment x -> xt was already inside the box (both ends are), so shrinking it needs no projection
+#pragma unroll
+          for (int j = 0; j < NQ; ++j)
+            if (j < n) xt[j * T] = fma(ratio, dx[j], xv[j]);
+          alpha = an;
+        }
+      }
+    }
+    if (done) {
+      const double* xf = vecp(2 * cur);
+      A.out_loss[pid] = f;
+      A.out_iters[pid] = A.debug ? (iter | (reason << 24)) : iter;
+      for (int j = 0; j < n; ++j) A.out_x[pid * n + j] = xf[j * T];
+      if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + t, 1);
+      state = AST_IDLE;
+    }
+  }
+  if (A.out_evals && evals) atomicAdd(A.out_evals, evals);
+}
+
 }  // namespace slam
 
 using namespace slam;
@@ -647,7 +970,11 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved; A.ws = ws; A.T = T;
   if (central == 2) {
-    if (n <= 32) adj_lbfgs_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+    if (n <= 16) adj_lbfgs_reg_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+    else if (n <= 24) adj_lbfgs_reg_kernel<24><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+    else if (n <= 32) adj_lbfgs_reg_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+    // (a 48-entry register form was measured: 3.8 KB of spills around the 255-register evaluation, 6.3 vs 7.6 M evaluations/s
+    //  on the sqCNOT k = 4 template, P = 42 -- the local-array form keeps the larger templates)
     else if (n <= 96) adj_lbfgs_kernel<96><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
     else adj_lbfgs_kernel<SLAM_MAX_PARAMS><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
   }
