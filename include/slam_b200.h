@@ -164,7 +164,10 @@ typedef struct SlamOptOpts {
      trace_loss[p*trace_cap + i-1] and the parameters in trace_x[(p*trace_cap + i-1)*P ...]; out_iters gives the
      number of iterations.  [dev] pointers, NULL / 0 = off.                                                      */
   int32_t trace_cap;
-  int32_t reserved;
+  int32_t diag;          /* slam_fd_lbfgs_solve diagnostics, 0 = off: 1 = out_iters carries the stop reason in bits 24-31
+                            (1 f_stop, 2 gtol, 3 gtol_far, 4 max_iter, 5 non-finite, 6 target solved elsewhere, 7 no feasible
+                            descent, 8 line search exhausted, 9 evaluation budget); 2 = as 1 with the problem's evaluation count
+                            (instead of its iterations) in bits 0-23                                                        */
   double* trace_loss;
   double* trace_x;
   /* optional box bounds, [dev] double[P] each: projected L-BFGS, replacing the reference's switch to scipy L-BFGS-B

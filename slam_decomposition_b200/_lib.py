@@ -53,7 +53,7 @@ class SlamOptOpts(C.Structure):
         ("x0_lo", C.c_double),
         ("x0_hi", C.c_double),
         ("trace_cap", C.c_int32),
-        ("reserved", C.c_int32),
+        ("diag", C.c_int32),
         ("trace_loss", C.c_void_p),
         ("trace_x", C.c_void_p),
         ("lower", C.c_void_p),

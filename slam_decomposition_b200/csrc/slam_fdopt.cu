@@ -303,6 +303,11 @@ enum { AST_IDLE = 0, AST_INIT = 1, AST_LS = 2 };
 // the previous store (possible aliasing), which serialised ~1700 L2 round trips per tick and left the evaluations with 15 %
 // of the time.  Every loop below either only loads from global memory (pipelined, unrolled) or only stores to it, and the
 // axpy of one history pair is fused with the dot product of the next (m + 1 dependent passes per loop instead of 2 m).
+// A line search that fails (31 backtracks) restarts from steepest descent.  On a landscape where only tiny steps succeed that
+// cycle -- SD step accepted after many backtracks, next quasi-Newton step rejected 31 times -- costs ~60 evaluations per
+// iteration for up to max_iter iterations, and the phase-locked CTA waits for it (measured: one such restart turned a 0.1 s
+// launch of the configs[3] grid into 4 s).  scipy's BFGS stops at its FIRST line-search failure; a few more are allowed here.
+constexpr int kMaxLsFail = 4;
 constexpr int kAdjCta = 256;  // one CTA per SM (the evaluation needs ~255 registers), phase-locked
 constexpr int kAdjHist = kFdHist;  // (s, y) pairs kept, in double.  Six float pairs were measured: +16 % evaluations/s (the
                                    // history loads are what the bookkeeping waits for: 52 % of the stall samples, 109 MB of
@@ -326,7 +331,9 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
   const bool bounded = A.lower != nullptr;
 
   int state = AST_IDLE, cur = 0, iter = 0, hcount = 0, hpos = 0, ls = 0;
-  bool exhausted = false, slow = false;
+  bool exhausted = false, slow = false, dir_sd = false;
+  int pevals = 0;  // evaluations of the current problem (diagnostics)
+  int nfail = 0;   // failed line searches of the current problem
   int64_t pid = 0, t = 0;
   double f = 0.0, alpha = 1.0, gde = 0.0, gamma = 1.0, f_chk = 0.0;
   double rho[kAdjHist], alp[kAdjHist];
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
         x1[j * T] = x;
       }
       state = AST_INIT;
-      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false;
+      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false; pevals = 0; nfail = 0;
     }
     // CTA-wide vote = the tick barrier: the CTA's warps enter the evaluation together and, with the barriers inside it,
     // walk through its 200 KB of code in step (one instruction stream through the 32 KB instruction cache instead of eight)
@@ -377,6 +384,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
     const double ft = adj1_nl_sync(&kt, xt, T, A.V + t * 32, A.cost_kind, gt, T);
     if (state == AST_IDLE) continue;
     ++evals;
+    ++pevals;
 
     // ---------------- bookkeeping ---------------------------------------------------------------------------
     const double* x = vecp(2 * cur);
@@ -504,8 +512,10 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
           gd = fma(t1[j], d, gd);  // (projected gradient; equals g.d on the free variables)
         }
         alpha = 1.0;
+        dir_sd = false;
         if (hcount == 0 || !(gd < 0.0)) {  // first step or not a descent direction: steepest descent, unit length
           hcount = 0;
+          dir_sd = true;
           for (int j = 0; j < n; ++j) dv[j] = -t1[j];
           alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
         }
@@ -533,8 +543,10 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
       }
       alpha = fmin(fmax(an, 0.1 * alpha), 0.5 * alpha);
       if (++ls > 30) {
-        if (hcount > 0) {  // curvature model is bad: restart from steepest descent
+        if (hcount > 0 && nfail < kMaxLsFail) {  // curvature model is bad: restart from steepest descent
+          ++nfail;
           hcount = 0;
+          dir_sd = true;
           double gg = 0.0;
 #pragma unroll 4
           for (int j = 0; j < n; ++j) {
@@ -554,31 +566,53 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
     }
     if (!done) {
       // next trial point x + alpha d (clamped to the box) into the non-current buffer, and the directional derivative
-      // along the (projected) segment for the Armijo test
+      // along the (projected) segment for the Armijo test.  A quasi-Newton direction whose clamped segment is not a descent
+      // segment falls back to projected steepest descent (as K5 does); only when that has no descent either is the point a
+      // KKT point of the box problem.
       const double* xc = vecp(2 * cur);
       const double* gc = xc + (int64_t)n * T;
       double* xn = vecp(2 * (cur ^ 1));
-      double g_step = 0.0;
+#pragma unroll 1
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        double g_step = 0.0;
 #pragma unroll 4
-      for (int j = 0; j < n; ++j) {
-        const double xj = xc[j * T];
-        double v = fma(alpha, dv[j], xj);
-        if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
-        t2[j] = v;
-        g_step = fma(gc[j * T], v - xj, g_step);
+        for (int j = 0; j < n; ++j) {
+          const double xj = xc[j * T];
+          double v = fma(alpha, dv[j], xj);
+          if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+          t2[j] = v;
+          g_step = fma(gc[j * T], v - xj, g_step);
+        }
+        gde = g_step;
+        if (gde < 0.0) break;
+        if (dir_sd) {  // zero (projected) gradient along the steepest-descent step
+          done = true;
+          reason = 7;
+          break;
+        }
+        dir_sd = true;
+        hcount = 0;
+        ls = 0;
+        double gg = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+          const double xj = xc[j * T], gj = gc[j * T];
+          double gp = gj;
+          if (bounded && ((xj <= A.lower[j] && gj > 0.0) || (xj >= A.upper[j] && gj < 0.0))) gp = 0.0;
+          dv[j] = -gp;
+          gg = fma(gp, gp, gg);
+        }
+        alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
       }
+      if (!done) {
 #pragma unroll 4
-      for (int j = 0; j < n; ++j) xn[j * T] = t2[j];
-      gde = g_step;
-      if (!(gde < 0.0)) {  // zero (projected) gradient along the step
-        done = true;
-        reason = 7;
+        for (int j = 0; j < n; ++j) xn[j * T] = t2[j];
       }
     }
     if (done) {
       const double* xf = vecp(2 * cur);
       A.out_loss[pid] = f;
-      A.out_iters[pid] = A.debug ? (iter | (reason << 24)) : iter;
+      A.out_iters[pid] = A.debug == 2 ? (min(pevals, 0xFFFFFF) | (reason << 24)) : A.debug ? (iter | (reason << 24)) : iter;
       for (int j = 0; j < n; ++j) A.out_x[pid * n + j] = xf[j * T];
       if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + t, 1);
       state = AST_IDLE;
@@ -617,6 +651,8 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
 
   int state = AST_IDLE, cur = 0, iter = 0, hcount = 0, hpos = 0, ls = 0;
   bool exhausted = false, slow = false;
+  int pevals = 0;  // evaluations of the current problem (diagnostics)
+  int nfail = 0;   // failed line searches of the current problem
   int64_t pid = 0, t = 0;
   double f = 0.0, alpha = 1.0, gd = 0.0, gamma = 1.0, f_chk = 0.0;
   double rho[kAdjHist];
@@ -653,7 +689,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         x1[j * T] = x;
       }
       state = AST_INIT;
-      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false;
+      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false; pevals = 0; nfail = 0;
     }
     if (__syncthreads_and(state == AST_IDLE)) break;  // CTA-wide vote = the tick barrier (phase lock, see above)
 
@@ -664,6 +700,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
     const double ft = adj1_nl_sync(&kt, xt, T, A.V + t * 32, A.cost_kind, gt, T);
     if (state == AST_IDLE) continue;
     ++evals;
+    ++pevals;
 
     // ---------------- bookkeeping (registers; every pass loads first, then computes) -------------------------
     const double* x = vecp(2 * cur);
@@ -790,40 +827,51 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         // d = -q ; g.d with the projected gradient (equals g.d on the free variables)
         double xa[NQ], ga[NQ];
         load_row(xt, xa);
-        load_row(gt, ga);
-        project(ga, xa);
+        load_row(gt, ga);  // (un-projected: the directional derivative along the clamped segment uses it)
+        auto gproj = [&](int j) -> double {  // projected gradient component j at the accepted point
+          if (bounded && j < n && ((xa[j] <= A.lower[j] && ga[j] > 0.0) || (xa[j] >= A.upper[j] && ga[j] < 0.0))) return 0.0;
+          return ga[j];
+        };
         double gdn = 0.0;
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
           q[j] = -q[j];
-          gdn = fma(ga[j], q[j], gdn);
+          gdn = fma(gproj(j), q[j], gdn);
         }
-        alpha = 1.0;
-        if (hcount == 0 || !(gdn < 0.0)) {  // first step or not a descent direction: steepest descent, unit length
-          hcount = 0;
-#pragma unroll
-          for (int j = 0; j < NQ; ++j) q[j] = -ga[j];
-          alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
-        }
+        bool use_sd = hcount == 0 || !(gdn < 0.0);  // first step or not a descent direction: steepest descent, unit length
         ls = 0;
         state = AST_LS;
-        // next trial point xt + alpha d (clamped to the box) into the other buffer; directional derivative along the
-        // (projected) segment per unit alpha, as the Armijo test and the cubic use it
-        load_row(gt, ga);  // (un-projected)
         double* xn = vecp(2 * (cur ^ 1));
-        double g_step = 0.0;
+        // next trial point xt + alpha d (clamped to the box) into the other buffer; directional derivative along the
+        // (projected) segment per unit alpha, as the Armijo test and the cubic use it.  A quasi-Newton direction whose
+        // clamped segment is not a descent segment falls back to projected steepest descent (as K5 does); only when that
+        // has no descent either is the point a KKT point of the box problem.
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; ++attempt) {
+          alpha = 1.0;
+          if (use_sd) {
+            hcount = 0;
 #pragma unroll
-        for (int j = 0; j < NQ; ++j)
-          if (j < n) {
-            double v = fma(alpha, q[j], xa[j]);
-            if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
-            xn[j * T] = v;
-            g_step = fma(ga[j], v - xa[j], g_step);
+            for (int j = 0; j < NQ; ++j) q[j] = -gproj(j);
+            alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
           }
-        gd = g_step / alpha;
-        if (!(gd < 0.0)) {  // zero (projected) gradient along the step
-          done = true;
-          reason = 7;
+          double g_step = 0.0;
+#pragma unroll
+          for (int j = 0; j < NQ; ++j)
+            if (j < n) {
+              double v = fma(alpha, q[j], xa[j]);
+              if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
+              xn[j * T] = v;
+              g_step = fma(ga[j], v - xa[j], g_step);
+            }
+          gd = g_step / alpha;
+          if (gd < 0.0) break;
+          if (use_sd) {  // zero (projected) gradient along the steepest-descent step
+            done = true;
+            reason = 7;
+            break;
+          }
+          use_sd = true;
         }
       }
     } else {
@@ -858,7 +906,8 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         const double ratio = an / alpha;
         bool restart_sd = false;
         if (++ls > 30) {
-          if (hcount > 0) {  // curvature model is bad: restart from steepest descent at the current point
+          if (hcount > 0 && nfail < kMaxLsFail) {  // curvature model is bad: restart from steepest descent at the current point
+            ++nfail;
             hcount = 0;
             restart_sd = true;
             ls = 0;
@@ -901,7 +950,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
     if (done) {
       const double* xf = vecp(2 * cur);
       A.out_loss[pid] = f;
-      A.out_iters[pid] = A.debug ? (iter | (reason << 24)) : iter;
+      A.out_iters[pid] = A.debug == 2 ? (min(pevals, 0xFFFFFF) | (reason << 24)) : A.debug ? (iter | (reason << 24)) : iter;
       for (int j = 0; j < n; ++j) A.out_x[pid * n + j] = xf[j * T];
       if (A.early_exit && f < A.success_threshold) atomicExch(A.solved + t, 1);
       state = AST_IDLE;
@@ -961,7 +1010,7 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit; A.central = central;
   // smush gates carry no circuit_fidelity factor, so 1 - BasicCostInverse x 1 is BasicCost (optimizer.py:200-201)
   if (central == 2 && A.cost_kind == SLAM_COST_BASIC_INVERSE) A.cost_kind = SLAM_COST_BASIC;
-  A.debug = 0;
+  A.debug = opts->diag;  // stop-reason / evaluation-count packing in out_iters (see SlamOptOpts.diag)
   A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
   A.lower = opts->lower;

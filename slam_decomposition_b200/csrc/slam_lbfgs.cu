@@ -65,7 +65,7 @@ extern "C" void slam_opt_defaults(SlamOptOpts* o) {
   o->x0_lo = 0.0;                // basis.py:111: np.random.random(P) * 2 pi
   o->x0_hi = 6.283185307179586;
   o->trace_cap = 0;
-  o->reserved = 0;
+  o->diag = 0;
   o->trace_loss = nullptr;
   o->trace_x = nullptr;
   o->lower = nullptr;

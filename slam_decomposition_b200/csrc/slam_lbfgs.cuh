@@ -421,12 +421,14 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
       }
     }
 
-    // ---------------- backtrack path (all lanes execute; effects predicated on `rejected`) ---------
-    {
+    // ---------------- backtrack path (warp-uniform branch; effects predicated on `rejected`) ------------
+    // Most ticks no team of the warp has a rejected trial (L-BFGS steps are usually accepted at alpha = 1), so the whole
+    // section sits behind a warp vote; inside it every lane executes every reduction (full-mask shuffles stay legal).
+    if (__any_sync(FULL, rejected)) {
       // cubic through (0, f, gd) and (alpha, ft, gdt), safeguarded to [0.1, 0.5] alpha; the direction is recovered
       // from the failed trial point: d = (xt - x) / alpha
       double dx[NPL];
-      double gdt = 0.0, gg = 0.0;
+      double gdt = 0.0;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
         dx[i] = 0.0;
@@ -434,16 +436,17 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
           const int j = sub + LPP * i;
           dx[i] = xt[j] - x[j];
           gdt = fma(gt[j], dx[i], gdt);
-          gg = fma(g[j], g[j], gg);
         }
       }
       gdt = team_sum<LPP>(gdt);
-      gg = team_sum<LPP>(gg);
+      double ratio = 0.0;
+      bool sd = false;  // curvature model is bad: restart from steepest descent
       if (rejected) {
-        gdt /= alpha;
+        const double ia = 1.0 / alpha;
+        gdt *= ia;
         double an = 0.5 * alpha;
         if (ft == ft && gdt == gdt) {
-          const double d1 = gd + gdt - 3.0 * (ft - f) / alpha;
+          const double d1 = gd + gdt - 3.0 * (ft - f) * ia;
           const double disc = d1 * d1 - gd * gdt;
           if (disc >= 0.0) {
             const double d2 = sqrt(disc);
@@ -455,28 +458,35 @@ __global__ void __launch_bounds__(MAXT, 1) lbfgs_kernel(const __grid_constant__ 
           }
         }
         an = fmin(fmax(an, 0.1 * alpha), 0.5 * alpha);
-        double ratio = an / alpha;
+        ratio = an * ia;
         alpha = an;
         ++ls;
         if (ls > 30) {
-          if (hcount > 0) {  // curvature model is bad: restart from steepest descent
-            hcount = 0;
-#pragma unroll
-            for (int i = 0; i < NPL; ++i)
-              if (EXACT || i < npl) dx[i] = -g[sub + LPP * i];
-            gd = -gg;
-            alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
-            ratio = alpha;
-            ls = 0;
-          } else {
-            done = true;  // no progress possible at working precision
-          }
+          if (hcount > 0) sd = true;
+          else done = true;  // no progress possible at working precision
         }
-        if (!done) {
+      }
+      if (__any_sync(FULL, sd)) {  // rare
+        double gg = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+          if (EXACT || i < npl) gg = fma(g[sub + LPP * i], g[sub + LPP * i], gg);
+        gg = team_sum<LPP>(gg);
+        if (sd) {
+          hcount = 0;
 #pragma unroll
           for (int i = 0; i < NPL; ++i)
-            if (EXACT || i < npl) xt[sub + LPP * i] = fma(ratio, dx[i], x[sub + LPP * i]);
+            if (EXACT || i < npl) dx[i] = -g[sub + LPP * i];
+          gd = -gg;
+          alpha = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
+          ratio = alpha;
+          ls = 0;
         }
+      }
+      if (rejected && !done) {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i)
+          if (EXACT || i < npl) xt[sub + LPP * i] = fma(ratio, dx[i], x[sub + LPP * i]);
       }
     }
     if (done) {

@@ -176,3 +176,35 @@ def test_bounded_adjoint_run_respects_the_box():
     loss, x, _ = engine.fd_lbfgs_solve(basis.desc, V, R, opts, seed=4, central="adjoint")
     assert x.min().item() >= -1.0 and x.max().item() <= 1.0
     assert (loss.min(dim=1).values <= 1e-9).float().mean().item() >= 0.75
+
+
+def test_bounded_adjoint_run_stops_only_at_kkt_points():
+    """Box-constrained K5c (adjoint mode; the reference switches scipy to L-BFGS-B, optimizer.py:257-258): a quasi-Newton
+    direction whose clamped segment is not a descent segment must fall back to projected steepest descent instead of
+    ending the restart (SlamOptOpts.diag exposes the stop reason: 7 = no feasible descent).  With the start box wider
+    than the bounds most initial points sit on a face of the box, which is where the premature stop used to happen."""
+    basis, orc = _smush_pair("sqiSwap", 1)
+    rng = np.random.default_rng(21)
+    Nt, R, P = 64, 8, orc.n_params
+    V = torch.as_tensor(np.stack([orc.eval(rng.uniform(-0.9, 0.9, P)) for _ in range(Nt)]), device="cuda")
+    lo = torch.full((P,), -1.0, dtype=torch.float64, device="cuda")
+    hi = torch.full((P,), 1.0, dtype=torch.float64, device="cuda")
+    opts = engine.opt_defaults()
+    opts.lower, opts.upper = lo.data_ptr(), hi.data_ptr()
+    opts.x0_lo, opts.x0_hi = -3.0, 3.0  # clamped into the box: many coordinates start on a bound
+    opts.early_exit = 0
+    opts.diag = 1
+    loss, x, it = engine.fd_lbfgs_solve(basis.desc, V, R, opts, seed=5, central="adjoint")
+    reason = (it.cpu().numpy().astype(np.int64) >> 24).ravel()
+    assert set(np.unique(reason)) <= {1, 2, 3, 4, 7, 8}, np.unique(reason)
+    assert x.min().item() >= -1.0 and x.max().item() <= 1.0
+    # every "no feasible descent" stop is a KKT point of the box problem: zero projected gradient
+    stop7 = np.nonzero(reason == 7)[0]
+    if len(stop7):
+        xs = x.reshape(-1, P)[torch.as_tensor(stop7, device="cuda")].contiguous()
+        _, g, _ = engine.loss_grad(basis.desc, xs, V, tgt_idx=torch.as_tensor(stop7 // R, dtype=torch.int32, device="cuda"))
+        xs_, g_ = xs.cpu().numpy(), g.cpu().numpy()
+        free = ~(((xs_ <= -1.0) & (g_ > 0)) | ((xs_ >= 1.0) & (g_ < 0)))
+        assert np.abs(g_ * free).max() < 1e-6
+    assert (reason == 7).mean() < 0.05, np.bincount(reason)
+    assert (loss.min(dim=1).values <= 1e-9).float().mean().item() >= 0.75
