@@ -150,7 +150,8 @@ int slam_weyl(const double* U, int64_t B, double* c, double* g, int32_t flags, v
  */
 typedef struct SlamOptOpts {
   int32_t max_iter;      /* per restart; reference: options={"maxiter": 2500}                    */
-  int32_t history;       /* L-BFGS pairs kept (<= 8); 0 = auto from shared-memory budget         */
+  int32_t history;       /* L-BFGS pairs kept (<= 8); 0 = auto (slam_lbfgs_solve: from the shared-memory budget;
+                            slam_fd_lbfgs_solve adjoint mode: 8 for P <= 32, else 5; its finite-difference modes always keep 8)           */
   int32_t cost_kind;     /* SlamCostKind                                                         */
   int32_t early_exit;    /* 1: other restarts of a target stop once one is < success_threshold   */
   double success_threshold; /* reference SUCCESS_THRESHOLD = 1e-10 (optimizer.py:18)             */
@@ -166,7 +167,7 @@ typedef struct SlamOptOpts {
   int32_t trace_cap;
   int32_t diag;          /* slam_fd_lbfgs_solve diagnostics, 0 = off: 1 = out_iters carries the stop reason in bits 24-31
                             (1 f_stop, 2 gtol, 3 gtol_far, 4 max_iter, 5 non-finite, 6 target solved elsewhere, 7 no feasible
-                            descent, 8 line search exhausted, 9 evaluation budget); 2 = as 1 with the problem's evaluation count
+                            descent, 8 line search exhausted, 9 stalled: < 3 % progress over 32 iterations at > 6 evaluations each); 2 = as 1 with the problem's evaluation count
                             (instead of its iterations) in bits 0-23                                                        */
   double* trace_loss;
   double* trace_x;

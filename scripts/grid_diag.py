@@ -11,7 +11,7 @@ from slam_decomposition_b200.optimizer import TemplateOptimizer
 from scripts.smush_training_grid import make_basis
 
 REASONS = {0: "none/skipped", 1: "f_stop", 2: "gtol", 3: "gtol_far", 4: "max_iter", 5: "non-finite", 6: "solved elsewhere",
-           7: "no feasible descent", 8: "line search exhausted", 9: "evaluation budget"}
+           7: "no feasible descent", 8: "line search exhausted", 9: "stalled"}
 
 
 def main():

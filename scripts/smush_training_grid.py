@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--targets", type=int, default=4096)
     ap.add_argument("--restarts", type=int, default=8)
     ap.add_argument("--fd", action="store_true")
+    ap.add_argument("--history", type=int, default=0, help="L-BFGS pairs kept (0 = automatic)")
     ap.add_argument("--build-only", action="store_true")
     args = ap.parse_args()
     grid = (0.25, 0.5, 0.75, 1.0, 1.25, 1.5)
@@ -57,6 +58,8 @@ def main():
         V = np.concatenate([own, bench.haar_targets(args.targets - half, 7)])
         opt = TemplateOptimizer(basis=basis, objective=BasicCost(), override_fail=True, training_restarts=args.restarts)
         opt.smush_adjoint = not args.fd
+        if args.history:
+            opt.tune = {"history": args.history}
         opt.approximate_targets(V[:64], range(1, 2))  # warm-up
         torch.cuda.synchronize(); t0 = time.perf_counter()
         out = opt.approximate_targets(V, range(1, 2))

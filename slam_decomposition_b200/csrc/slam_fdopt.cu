@@ -37,6 +37,7 @@ struct FdArgs {
   const int32_t* active;
   int64_t Nt;
   int restarts, max_iter, cost_kind, early_exit, central, debug;
+  int m;  // (s, y) pairs kept by the adjoint kernels (<= kAdjHist); the finite-difference kernel keeps kFdHist
   double success_threshold, f_stop, gtol, gtol_far, f_far, x0_lo, x0_span;
   const double* lower;
   const double* upper;
@@ -308,6 +309,12 @@ enum { AST_IDLE = 0, AST_INIT = 1, AST_LS = 2 };
 // iteration for up to max_iter iterations, and the phase-locked CTA waits for it (measured: one such restart turned a 0.1 s
 // launch of the configs[3] grid into 4 s).  scipy's BFGS stops at its FIRST line-search failure; a few more are allowed here.
 constexpr int kMaxLsFail = 4;
+// A restart at a clearly non-zero loss (f > f_far) that, over a window of 32 accepted iterations, improved the loss by < 3 %
+// AND needed more than kStallEvals evaluations per iteration (i.e. nearly every line search backtracked many times) is
+// crawling along a ridge: it ends with stop reason 9.  (Restarts creeping towards a zero of the loss are left alone.)  Measured on the configs[3] grid: 3 of 196608 restarts did this for all 2500 iterations at ~19 evaluations
+// each (48 k evaluations, 3 - 6 s of a phase-locked CTA waiting for ONE thread, against 0.1 - 0.3 s for the whole launch).
+// scipy ends such a restart at its first failed line search (maxls = 20 evaluations).
+constexpr int kStallEvals = 6;
 constexpr int kAdjCta = 256;  // one CTA per SM (the evaluation needs ~255 registers), phase-locked
 constexpr int kAdjHist = kFdHist;  // (s, y) pairs kept, in double.  Six float pairs were measured: +16 % evaluations/s (the
                                    // history loads are what the bookkeeping waits for: 52 % of the stall samples, 109 MB of
@@ -319,7 +326,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <int NQ>
 __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_constant__ FdArgs A, const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
-  const int m = kAdjHist;
+  const int m = A.m;
   const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t T = A.T;
   double* ws = A.ws + tidg;
@@ -334,6 +341,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
   bool exhausted = false, slow = false, dir_sd = false;
   int pevals = 0;  // evaluations of the current problem (diagnostics)
   int nfail = 0;   // failed line searches of the current problem
+  int pe_chk = 0;  // pevals at the last progress checkpoint
   int64_t pid = 0, t = 0;
   double f = 0.0, alpha = 1.0, gde = 0.0, gamma = 1.0, f_chk = 0.0;
   double rho[kAdjHist], alp[kAdjHist];
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
         x1[j * T] = x;
       }
       state = AST_INIT;
-      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false; pevals = 0; nfail = 0;
+      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false; pevals = 0; nfail = 0; pe_chk = 0;
     }
     // CTA-wide vote = the tick barrier: the CTA's warps enter the evaluation together and, with the barriers inside it,
     // walk through its 200 KB of code in step (one instruction stream through the 32 KB instruction cache instead of eight)
@@ -396,11 +404,20 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
       // ---- accept ----
       // t1 <- projected gradient at the accepted point (also the start of the two-loop recursion); history pair
       double gmax = 0.0, gg = 0.0, sy = 0.0, yy = 0.0;
+      // active set of this iteration (variables on a bound with the gradient pushing outward): the two-loop recursion runs
+      // in the free subspace, see adj_lbfgs_reg_kernel
+      unsigned act[(NQ + 31) / 32];
+#pragma unroll
+      for (int w = 0; w < (NQ + 31) / 32; ++w) act[w] = 0;
+      auto is_act = [&](int j) -> bool { return bounded && ((act[j >> 5] >> (j & 31)) & 1u); };
 #pragma unroll 4
       for (int j = 0; j < n; ++j) {
         const double xtj = xt[j * T], gtj = gt[j * T];
         double gp = gtj;
-        if (bounded && ((xtj <= A.lower[j] && gtj > 0.0) || (xtj >= A.upper[j] && gtj < 0.0))) gp = 0.0;
+        if (bounded && ((xtj <= A.lower[j] && gtj > 0.0) || (xtj >= A.upper[j] && gtj < 0.0))) {
+          gp = 0.0;
+          act[j >> 5] |= 1u << (j & 31);
+        }
         t1[j] = gp;
         gmax = fmax(gmax, fabs(gp));
         gg = fma(gp, gp, gg);
@@ -434,9 +451,12 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
       }
       cur ^= 1;  // the trial point becomes the current point
       f = ft;
+      bool stalled = false;
       if (!first && (iter & 31) == 0) {  // progress checkpoint (same rule as the sequential form)
         slow = f > 0.97 * f_chk;
         f_chk = f;
+        stalled = slow && f > A.f_far && pevals - pe_chk > 32 * kStallEvals;  // crawling: see kStallEvals
+        pe_chk = pevals;
       }
       if (f < A.f_stop) reason = 1;
       else if (gmax < A.gtol) reason = 2;
@@ -444,6 +464,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
       else if (iter >= A.max_iter) reason = 4;
       else if (!(f == f)) reason = 5;
       else if (A.early_exit && (iter & 3) == 0 && *((volatile int32_t*)(A.solved + t)) != 0) reason = 6;
+      else if (stalled) reason = 9;
       done = reason != 0;
       if (!done) {
         // two-loop recursion, q = dv <- t1.  First loop, newest to oldest: a_i = rho_i s_i.q ; q -= a_i y_i -- the axpy of
@@ -469,8 +490,9 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
           double acc = 0.0;
 #pragma unroll 4
           for (int j = 0; j < n; ++j) {
-            const double qj = hh == 0 ? dv[j] : fma(-a_prev, y_prev[j * T], dv[j]);  // (no load in the first pass: the
-                                                                                     // history may be uninitialised)
+            double qj = hh == 0 ? dv[j] : fma(-a_prev, y_prev[j * T], dv[j]);  // (no load in the first pass: the
+                                                                               // history may be uninitialised)
+            if (is_act(j)) qj = 0.0;
             dv[j] = qj;
             acc = fma(sk[j * T], qj, acc);
           }
@@ -495,7 +517,8 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
           double acc = 0.0;
 #pragma unroll 4
           for (int j = 0; j < n; ++j) {
-            const double rj = firstpass ? scale0 * dv[j] : fma(c_prev, s_prev[j * T], dv[j]);
+            double rj = firstpass ? scale0 * dv[j] : fma(c_prev, s_prev[j * T], dv[j]);
+            if (is_act(j)) rj = 0.0;
             dv[j] = rj;
             acc = fma(yk[j * T], rj, acc);
           }
@@ -639,7 +662,7 @@ template <int NQ>
 __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_constant__ FdArgs A,
                                                                    const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
-  constexpr int m = kAdjHist;
+  const int m = A.m;
   const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t T = A.T;
   double* ws = A.ws + tidg;
@@ -653,6 +676,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
   bool exhausted = false, slow = false;
   int pevals = 0;  // evaluations of the current problem (diagnostics)
   int nfail = 0;   // failed line searches of the current problem
+  int pe_chk = 0;  // pevals at the last progress checkpoint
   int64_t pid = 0, t = 0;
   double f = 0.0, alpha = 1.0, gd = 0.0, gamma = 1.0, f_chk = 0.0;
   double rho[kAdjHist];
@@ -689,7 +713,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         x1[j * T] = x;
       }
       state = AST_INIT;
-      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false; pevals = 0; nfail = 0;
+      iter = 0; ls = 0; hcount = 0; hpos = 0; gamma = 1.0; slow = false; pevals = 0; nfail = 0; pe_chk = 0;
     }
     if (__syncthreads_and(state == AST_IDLE)) break;  // CTA-wide vote = the tick barrier (phase lock, see above)
 
@@ -724,6 +748,20 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
       // ---- accept ----
       double q[NQ];  // projected gradient at the accepted point, then the two-loop working vector
       double gmax = 0.0, gg = 0.0, sy = 0.0, yy = 0.0;
+      // Active set of this iteration: variables on a bound whose gradient pushes outward.  The two-loop recursion runs in
+      // the FREE subspace -- the working vector is masked after every update -- so the quasi-Newton direction never moves an
+      // active variable and is a model step of the free variables only.  Projecting the full-space direction instead (the
+      // clamp then discards its active components) leaves a step the free variables were never meant to take alone: measured
+      // on the configs[3] grid, most restarts that reached a face of the +-2 pi amplitude box got non-descent segments and
+      // degenerated to steepest descent (6 % ran into max_iter).
+      unsigned act = 0;
+      auto mask_q = [&]() {
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < NQ; ++j)
+            if (act & (1u << j)) q[j] = 0.0;
+        }
+      };
       {
         double a[NQ], b[NQ];
         if (!first) {
@@ -750,7 +788,12 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         }
         if (bounded) {
           load_row(xt, b);
-          project(q, b);
+#pragma unroll
+          for (int j = 0; j < NQ; ++j)
+            if (j < n && ((b[j] <= A.lower[j] && q[j] > 0.0) || (b[j] >= A.upper[j] && q[j] < 0.0))) {
+              q[j] = 0.0;
+              act |= 1u << j;
+            }
         }
       }
 #pragma unroll
@@ -773,9 +816,12 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
       }
       cur ^= 1;  // the trial point becomes the current point
       f = ft;
+      bool stalled = false;
       if (!first && (iter & 31) == 0) {  // progress checkpoint (same rule as the local-array form)
         slow = f > 0.97 * f_chk;
         f_chk = f;
+        stalled = slow && f > A.f_far && pevals - pe_chk > 32 * kStallEvals;  // crawling: see kStallEvals
+        pe_chk = pevals;
       }
       if (f < A.f_stop) reason = 1;
       else if (gmax < A.gtol) reason = 2;
@@ -783,6 +829,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
       else if (iter >= A.max_iter) reason = 4;
       else if (!(f == f)) reason = 5;
       else if (A.early_exit && (iter & 3) == 0 && *((volatile int32_t*)(A.solved + t)) != 0) reason = 6;
+      else if (stalled) reason = 9;
       done = reason != 0;
       if (!done) {
         // two-loop recursion on the register vector: per pair one fully unrolled load pass for s and one for y
@@ -803,6 +850,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
           load_row(hy(slot), v);
 #pragma unroll
           for (int j = 0; j < NQ; ++j) q[j] = fma(-a, v[j], q[j]);
+          mask_q();
         }
         if (hcount > 0) {
 #pragma unroll
@@ -823,6 +871,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
           load_row(hs(slot), v);
 #pragma unroll
           for (int j = 0; j < NQ; ++j) q[j] = fma(c, v[j], q[j]);
+          mask_q();
         }
         // d = -q ; g.d with the projected gradient (equals g.d on the free variables)
         double xa[NQ], ga[NQ];
@@ -972,6 +1021,7 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   if (opts->cost_kind != SLAM_COST_BASIC && opts->cost_kind != SLAM_COST_SQUARE && opts->cost_kind != SLAM_COST_BASIC_INVERSE)
     return SLAM_ERR_UNSUPPORTED;  // the coordinate-based functionals are piecewise constant (8-dp rounding): no gradient
   if (opts->max_iter < 1 || desc->n_params < 1 || central < 0 || central > 2) return SLAM_ERR_INVALID;
+  if (opts->history < 0 || opts->history > kFdHist) return SLAM_ERR_INVALID;
   if ((opts->lower == nullptr) != (opts->upper == nullptr)) return SLAM_ERR_INVALID;  // box = both arrays (+-inf allowed)
   if (Nt == 0) return SLAM_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1010,6 +1060,11 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit; A.central = central;
   // smush gates carry no circuit_fidelity factor, so 1 - BasicCostInverse x 1 is BasicCost (optimizer.py:200-201)
   if (central == 2 && A.cost_kind == SLAM_COST_BASIC_INVERSE) A.cost_kind = SLAM_COST_BASIC;
+  // history of the adjoint kernels, measured (scripts/k5c_bench.py, 131072 x 8 restarts; scripts/k5c_basin_check.py): for P <= 32
+  // (register form) 8 -> 6 pairs is flat to 12 % faster but costs 7 - 9 % more evaluations and, on the singular-Hessian
+  // in-basin problem of the tests, 2 of 12 targets no longer reach 1e-10 -- 8 stays; for the local-array form (P = 42) 5 pairs
+  // are 16 % faster than 8 at an unchanged solved fraction
+  A.m = opts->history > 0 ? std::min<int>(opts->history, kAdjHist) : (n <= 32 ? kAdjHist : 5);
   A.debug = opts->diag;  // stop-reason / evaluation-count packing in out_iters (see SlamOptOpts.diag)
   A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;

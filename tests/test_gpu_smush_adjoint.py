@@ -196,7 +196,7 @@ def test_bounded_adjoint_run_stops_only_at_kkt_points():
     opts.diag = 1
     loss, x, it = engine.fd_lbfgs_solve(basis.desc, V, R, opts, seed=5, central="adjoint")
     reason = (it.cpu().numpy().astype(np.int64) >> 24).ravel()
-    assert set(np.unique(reason)) <= {1, 2, 3, 4, 7, 8}, np.unique(reason)
+    assert set(np.unique(reason)) <= {1, 2, 3, 4, 7, 8, 9}, np.unique(reason)
     assert x.min().item() >= -1.0 and x.max().item() <= 1.0
     # every "no feasible descent" stop is a KKT point of the box problem: zero projected gradient
     stop7 = np.nonzero(reason == 7)[0]
