@@ -657,6 +657,14 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
 //     line search is in progress (as K5 does), so no thread-local arrays exist at all.
 // (x, g) double-buffered and the (s, y) history stay in the interleaved global workspace (entry j of thread t at [j T + t]:
 // every access of a warp is one coalesced line).
+// Measured and rejected on this kernel (scripts/k5c_bench.py, 131072 x 8 restarts, sqiSwap k = 2 / 3 smush templates):
+//   * 2 or 4 CTAs per SM instead of one phase-locked 256-thread CTA (so that one CTA's bookkeeping overlaps another's
+//     evaluation): 98 -> 81 -> 48 M evaluations/s -- the CTA-wide instruction stream through the ~300 KB of code matters more;
+//   * issuing the s and y row of a history pair together and prefetching every row of the two-loop recursion into L2 at the
+//     start of the bookkeeping: no change (2.27 s) -- with 8 warps per SM at 255 registers every warp issues one instruction
+//     per ~7 cycles (ncu: wait 1.9, long_scoreboard 1.2, no_instruction 1.0, barrier 0.7 per issue), so a tick costs the same
+//     ~0.25 ms whether one or all 256 threads are live; the lever is occupancy, which the 4x4 complex R, W, Q of the adjoint
+//     pass (192 registers) do not leave room for.
 // ------------------------------------------------------------------------------------------------------------------
 template <int NQ>
 __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_constant__ FdArgs A,

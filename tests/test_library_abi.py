@@ -206,3 +206,10 @@ def test_optimiser_option_validation_needs_no_device(lib):
     o = opts()
     o.con_mu = 1.0
     assert fd(o, 2, sdesc) == -2  # the constraint term is differenced, not adjoint
+    # the history length of the generic-objective solver is a runtime option, range checked; diag defaults to off
+    o = opts()
+    assert (o.history, o.diag) == (0, 0)
+    o.history = 9
+    assert fd(o, 2, sdesc) == -1 and lbfgs(o) == -1
+    o.history = -1
+    assert fd(o, 2, sdesc) == -1
