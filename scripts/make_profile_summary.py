@@ -32,22 +32,28 @@ for r in rows[2:]:
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--launch-count', '1'],
                      capture_output=True, text=True).stdout
 cur = None; agg = collections.Counter(); aggx = collections.Counter(); ai = ei = None
+reasons = collections.defaultdict(collections.Counter); ridx = {}
 for r in csv.reader(io.StringIO(src)):
     if not r: continue
     if r[0] == 'File Path': cur = r[1].split('/')[-1]; continue
     if r[0] == 'Line No':
-        ai = r.index('Warp Stall Sampling (All Samples)'); ei = r.index('Instructions Executed') if 'Instructions Executed' in r else None; continue
+        ai = r.index('Warp Stall Sampling (All Samples)'); ei = r.index('Instructions Executed') if 'Instructions Executed' in r else None
+        ridx = {i: c for i, c in enumerate(r) if c.startswith('stall_') and 'Not Issued' not in c}; continue
     if r[0].isdigit() and ai is not None:
         def I(v):
             try: return int(v)
             except ValueError: return 0
         k = (cur, int(r[0]), r[1].strip()[:100]); agg[k] += I(r[ai]); aggx[k] += I(r[ei]) if ei is not None else 0
+        for i, c in ridx.items():
+            if i < len(r): reasons[k][c[6:]] += I(r[i])
 tot = sum(agg.values()) or 1; totx = sum(aggx.values()) or 1
 lines.append("\n## first launch: warp-stall samples / executed warp instructions by source file")
 byf = collections.Counter(); byfx = collections.Counter()
 for k, v in agg.items(): byf[k[0]] += v; byfx[k[0]] += aggx[k]
 for f, v in byf.most_common(): lines.append(f"{f:28s} samples {100*v/tot:5.1f}%  exec {100*byfx[f]/totx:5.1f}%")
 lines.append("\n## hottest CUDA source lines (share of stall samples, share of executed instructions)")
-for k, v in agg.most_common(25): lines.append(f"{100*v/tot:5.1f}%  {100*aggx[k]/totx:5.1f}%  {k[0]}:{k[1]}  {k[2]}")
+for k, v in agg.most_common(25):
+    top = ' '.join(f'{n}:{100*c/max(1,sum(reasons[k].values())):.0f}%' for n, c in reasons[k].most_common(3))
+    lines.append(f"{100*v/tot:5.1f}%  {100*aggx[k]/totx:5.1f}%  {k[0]}:{k[1]}  {k[2]}   [{top}]")
 open(out, 'w').write("\n".join(lines) + "\n")
 print("wrote", out)

@@ -92,15 +92,47 @@ struct SmushGrad {
   double pa, pb, pc, pg, gc, gg, gz1, gz2, dt;
 };
 
-// Backward through one slice.  In: R[c] = column c of the right product INCLUDING the slice, W[c] = row c of the left
-// environment EXCLUDING it.  Out: R[c] without the slice, W[c] including it; *d_gx, *d_gy = d loss / d amplitudes of this
-// slice; gate-level derivatives accumulated into `acc`.
-// SYNC: CTA-wide barriers between the sub-phases (eigen-decomposition | into the eigenbasis | divided differences and G |
-// parameter derivatives and back-transform), each 5-15 KB of code: see slam_fwd1.cuh (fwd1_gate) for why.
-template <bool SYNC = false>
-__device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, double gy, double dt, cd R[4][4], cd W[4][4],
-                                                double* d_gx, double* d_gy, SmushGrad& acc) {
-  HermG A;
+// ---- eigen-decomposition hand-over from the forward to the backward sweep ---------------------------------------------
+// The backward pass needs H = Q diag(lam) Q^dagger of every slice.  When the forward sweep of the SAME evaluation also
+// exponentiates through it (E = Q e^{-i dt lam} Q^dagger, instead of the cos/sin series of slam_fwd1.cuh: about the same
+// cost, one Jacobi + two 4x4 products per slice) and keeps (Q, lam), the backward sweep skips its Jacobi -- half of a
+// slice's backward work, a quarter of the whole loss + gradient evaluation.  The 36 doubles per slice live in a
+// thread-local array (local memory: interleaved across the warp by the hardware, L1-cached), bounded to kEigSlices
+// slices; templates with more slices use the recomputing form.
+constexpr int kEigSlices = 8;
+struct NoEigStore {
+  static constexpr bool on = false;
+  __device__ __forceinline__ void put(int, const cd (*)[4], const double*) {}
+  __device__ __forceinline__ void get(int, cd (*)[4], double*) const {}
+};
+struct LocalEigStore {
+  static constexpr bool on = true;
+  double buf[kEigSlices * 36];
+  __device__ __forceinline__ void put(int slice, const cd (*Q)[4], const double* lam) {
+    double* p = buf + slice * 36;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        p[(a * 4 + i) * 2] = Q[a][i].re;
+        p[(a * 4 + i) * 2 + 1] = Q[a][i].im;
+      }
+      p[32 + a] = lam[a];
+    }
+  }
+  __device__ __forceinline__ void get(int slice, cd (*Q)[4], double* lam) const {
+    const double* p = buf + slice * 36;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Q[a][i] = mkc(p[(a * 4 + i) * 2], p[(a * 4 + i) * 2 + 1]);
+      lam[a] = p[32 + a];
+    }
+  }
+};
+
+// the slice generator of hamiltonian.py:114-182 as a general Hermitian 4x4 (same entries as smush_slice in slam_fwd1.cuh)
+__device__ __forceinline__ void smush_generator(const SmushGate& G, double gx, double gy, HermG& A) {
   A.d[0] = G.gz1 + G.gz2;
   A.d[1] = G.gz1;
   A.d[2] = G.gz2;
@@ -111,10 +143,70 @@ __device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, d
   A.u[3] = mkc(G.gc * G.ec.re, G.gc * G.ec.im);  // (1,2)
   A.u[4] = A.u[1];                               // (1,3)
   A.u[5] = A.u[0];                               // (2,3)
+}
+
+// Forward through one slice in eigen-form: R[c] <- Q e^{-i dt lam} Q^dagger R[c]; (Q, lam) handed to the backward sweep.
+template <bool SYNC, class ES>
+__device__ __forceinline__ void smush_slice_fwd_eig(const SmushGate& G, double gx, double gy, double dt, cd R[4][4], ES& es,
+                                                    int slice) {
+  HermG A;
+  smush_generator(G, gx, gy, A);
   cd Q[4][4];
   if (SYNC) __syncthreads();
   herm_eig4(A, Q);
   if (SYNC) __syncthreads();
+  es.put(slice, Q, A.d);
+  cd ph[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double s, c;
+    fast_sincos(-dt * A.d[a], &s, &c);
+    ph[a] = mkc(c, s);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    cd t[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      cd x = cmulc(R[c][0], Q[a][0]);  // (Q^dagger r)_a = sum_i conj(Q[a][i]) r_i
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        const cd z = cmulc(R[c][i], Q[a][i]);
+        x.re += z.re;
+        x.im += z.im;
+      }
+      t[a] = cmul(x, ph[a]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cd x = cmul(Q[0][i], t[0]);
+#pragma unroll
+      for (int a = 1; a < 4; ++a) cacc(x, Q[a][i], t[a]);
+      R[c][i] = x;
+    }
+  }
+}
+
+// Backward through one slice.  In: R[c] = column c of the right product INCLUDING the slice, W[c] = row c of the left
+// environment EXCLUDING it.  Out: R[c] without the slice, W[c] including it; *d_gx, *d_gy = d loss / d amplitudes of this
+// slice; gate-level derivatives accumulated into `acc`.
+// SYNC: CTA-wide barriers between the sub-phases (eigen-decomposition | into the eigenbasis | divided differences and G |
+// parameter derivatives and back-transform), each 5-15 KB of code: see slam_fwd1.cuh (fwd1_gate) for why.
+template <bool SYNC = false, class ES = NoEigStore>
+__device__ __forceinline__ void smush_slice_bwd(const SmushGate& G, double gx, double gy, double dt, cd R[4][4], cd W[4][4],
+                                                double* d_gx, double* d_gy, SmushGrad& acc, const ES& es = ES(),
+                                                int slice = 0) {
+  HermG A;
+  cd Q[4][4];
+  if (ES::on) {
+    if (SYNC) __syncthreads();
+    es.get(slice, Q, A.d);  // (Q, lam) of this slice from the forward sweep
+  } else {
+    smush_generator(G, gx, gy, A);
+    if (SYNC) __syncthreads();
+    herm_eig4(A, Q);
+    if (SYNC) __syncthreads();
+  }
   cd hp[4], ph[4];  // e^{-i dt lam / 2}, e^{-i dt lam}
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -294,16 +386,48 @@ struct StridedGrad {  // workspace vector interleaved across threads
 
 // ------------------------------------------------------------------------------------------------
 // loss + gradient of cost(template(x), V) for a GM_SMUSH template, one thread.
+//   ES = LocalEigStore: eigen-form forward sweep that hands (Q, lam) of every slice to the backward sweep (k T <= kEigSlices)
 //   ps.get(j)      : parameter j (API order)
 //   gs.set(j, v)   : d loss / d parameter j  (every parameter is bound to exactly one slot -- checked on the host --
 //                    so each entry is set once)
 // returns the loss; *T_out = Tr(V^dagger U) if non-null
 // ------------------------------------------------------------------------------------------------
-template <class PS, class GS, bool SYNC = false>
+// forward chain of a GM_SMUSH template with the slices in eigen-form (see LocalEigStore); slice index = gate * T + slice
+template <class PS, bool SYNC, class ES>
+__device__ __forceinline__ void fwd1_chain_eig(const KTemplate& kt, const PS& ps, cd R[4][4], ES& es) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) R[c][r] = mkc(c == r ? 1.0 : 0.0, 0.0);
+  const int Tn = kt.T;
+  const bool ph1q = kt.gate_kind == SLAM_GATE_SMUSH_1QPHASE;
+  const int o = ph1q ? 8 : 4;  // first gx slot
+  for (int i = 0; i <= kt.k; ++i) {
+    if (SYNC) __syncthreads();
+    fwd1_layer(kt, ps, i, R);
+    if (i < kt.k) {
+      const int g = i;
+      SmushGate G;
+      if (ph1q)
+        G = smush_gate(slot_val(kt, ps, g, 0), slot_val(kt, ps, g, 1), slot_val(kt, ps, g, 2), slot_val(kt, ps, g, 3),
+                       slot_val(kt, ps, g, 4), slot_val(kt, ps, g, 5), slot_val(kt, ps, g, 6), slot_val(kt, ps, g, 7));
+      else
+        G = smush_gate(0.0, 0.0, slot_val(kt, ps, g, 0), slot_val(kt, ps, g, 1), slot_val(kt, ps, g, 2),
+                       slot_val(kt, ps, g, 3), 0.0, 0.0);
+      const double dt = slot_val(kt, ps, g, o + 2 * Tn) / (double)Tn;
+      for (int it = 0; it < Tn; ++it)
+        smush_slice_fwd_eig<SYNC>(G, slot_val(kt, ps, g, o + it), slot_val(kt, ps, g, o + Tn + it), dt, R, es, g * Tn + it);
+    }
+  }
+}
+
+template <class PS, class GS, bool SYNC = false, class ES = NoEigStore>
 __device__ __forceinline__ double adj1_loss_grad(const KTemplate& kt, const PS& ps, const double* __restrict__ V,
                                                  int cost_kind, GS& gs, cd* T_out) {
   cd R[4][4];  // [col][row]
-  fwd1_chain<PS, GM_SMUSH, SYNC>(kt, ps, R);
+  ES es;
+  if (ES::on) fwd1_chain_eig<PS, SYNC>(kt, ps, R, es);
+  else fwd1_chain<PS, GM_SMUSH, SYNC>(kt, ps, R);
   cd T = mkc(0.0, 0.0);
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -401,7 +525,8 @@ __device__ __forceinline__ double adj1_loss_grad(const KTemplate& kt, const PS& 
       SmushGrad acc = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       for (int it = Tn - 1; it >= 0; --it) {
         double dgx, dgy;
-        smush_slice_bwd<SYNC>(G, slot_val(kt, ps, g, o + it), slot_val(kt, ps, g, o + Tn + it), dt, R, W, &dgx, &dgy, acc);
+        smush_slice_bwd<SYNC, ES>(G, slot_val(kt, ps, g, o + it), slot_val(kt, ps, g, o + Tn + it), dt, R, W, &dgx, &dgy, acc,
+                                  es, g * Tn + it);
         int p;
         if ((p = kt.slot_param[g][o + it]) >= 0) gs.set(p, dgx);
         if ((p = kt.slot_param[g][o + Tn + it]) >= 0) gs.set(p, dgy);

@@ -55,11 +55,23 @@ struct FdArgs {
 
 // out-of-line, phase-locked copy of the adjoint pass (loss + gradient of one workspace vector) for the tick kernel: every
 // thread of the CTA calls it in the same tick (CTA-wide barriers inside)
-static __device__ __noinline__ double adj1_nl_sync(const KTemplate* kt, const double* p, int64_t stride, const double* V,
-                                                   int cost_kind, double* g, int64_t gstride) {
+static __device__ __noinline__ double adj1_nl_sync_recompute(const KTemplate* kt, const double* p, int64_t stride, const double* V,
+                                                             int cost_kind, double* g, int64_t gstride) {
   StridedParams ps{p, stride};
   StridedGrad gsw{g, gstride};
   return adj1_loss_grad<StridedParams, StridedGrad, true>(*kt, ps, V, cost_kind, gsw, nullptr);
+}
+// eigen-form forward sweep handing (Q, lam) of every slice to the backward sweep (slam_adj1.cuh); k T <= kEigSlices
+static __device__ __noinline__ double adj1_nl_sync_eig(const KTemplate* kt, const double* p, int64_t stride, const double* V,
+                                                       int cost_kind, double* g, int64_t gstride) {
+  StridedParams ps{p, stride};
+  StridedGrad gsw{g, gstride};
+  return adj1_loss_grad<StridedParams, StridedGrad, true, LocalEigStore>(*kt, ps, V, cost_kind, gsw, nullptr);
+}
+static __device__ __forceinline__ double adj1_nl_sync(const KTemplate* kt, const double* p, int64_t stride, const double* V,
+                                                      int cost_kind, double* g, int64_t gstride) {
+  if (kt->k * kt->T <= kEigSlices) return adj1_nl_sync_eig(kt, p, stride, V, cost_kind, g, gstride);  // (uniform over the grid)
+  return adj1_nl_sync_recompute(kt, p, stride, V, cost_kind, g, gstride);
 }
 
 // MODE 0: forward differences (scipy's jac=None), 1: central differences.  (The analytic adjoint mode, central = 2 at the
@@ -647,7 +659,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
 
 // ------------------------------------------------------------------------------------------------------------------
 // K5c, adjoint mode, REGISTER form (P <= 32): the same tick-structured optimiser with the bookkeeping written like K5's.
-//   * the vector length bound NQ is a compile-time constant and every vector loop is fully unrolled with a `j < n` guard, so
+//   * the vector length bound NQ is a compile-time constant and every vector loop is fully unrolled over NQ padded entries, so
 //     the working vector of the two-loop recursion lives in REGISTERS and every pass issues all of its loads before the
 //     first use.  The local-array form above walks its vectors with a runtime bound: 4 loads in flight per thread, each an
 //     L2 / DRAM round trip of the interleaved workspace -- ncu: long_scoreboard 3.25 per issue, FP64 pipe 26 %
@@ -655,8 +667,8 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
 //     other warps' evaluations;
 //   * nothing vector-sized is carried across the evaluation: the search direction is recovered as (xt - x) / alpha while a
 //     line search is in progress (as K5 does), so no thread-local arrays exist at all.
-// (x, g) double-buffered and the (s, y) history stay in the interleaved global workspace (entry j of thread t at [j T + t]:
-// every access of a warp is one coalesced line).
+// (x, g) double-buffered and the (s, y) history stay in global memory, in a CTA-local interleaved chunk (entry j of thread t at
+// [j 256 + t]: every access of a warp is one coalesced line and every offset of an unrolled pass an immediate).
 // Measured and rejected on this kernel (scripts/k5c_bench.py, 131072 x 8 restarts, sqiSwap k = 2 / 3 smush templates):
 //   * 2 or 4 CTAs per SM instead of one phase-locked 256-thread CTA (so that one CTA's bookkeeping overlaps another's
 //     evaluation): 98 -> 81 -> 48 M evaluations/s -- the CTA-wide instruction stream through the ~300 KB of code matters more;
@@ -671,14 +683,27 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
                                                                    const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
   const int m = A.m;
-  const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t T = A.T;
-  double* ws = A.ws + tidg;
-  auto vecp = [&](int v) -> double* { return ws + (int64_t)v * n * T; };  // entry j at [j * T]
-  auto hs = [&](int slot) -> double* { return ws + (int64_t)(4 + slot) * n * T; };
-  auto hy = [&](int slot) -> double* { return ws + (int64_t)(4 + m + slot) * n * T; };
+  // CTA-local workspace chunk: vector v of thread t has its entry j at chunk[(v NQ + j) T + t], T = the CTA size -- a
+  // compile-time constant, so every access of an unrolled pass is ONE load / store with an immediate offset (j T 8 bytes)
+  // from the row pointer, still one coalesced line per warp.  Vectors are padded to NQ entries that stay zero, so the
+  // passes need no `j < n` guards either.  (With the grid-wide interleave [j T_grid + t] of the local-array form every
+  // element cost a 64-bit multiply-add, a compare and a select: ncu had this one line at 19 % of ALL executed instructions.)
+  constexpr int64_t T = kAdjCta;
+  constexpr int kVecs = 4 + 2 * kAdjHist;
+  double* ws = A.ws + (int64_t)blockIdx.x * (kVecs * NQ * T) + threadIdx.x;
+  auto vecp = [&](int v) -> double* { return ws + (int64_t)v * (NQ * T); };  // entry j at [j * T]
+  auto hs = [&](int slot) -> double* { return ws + (int64_t)(4 + slot) * (NQ * T); };
+  auto hy = [&](int slot) -> double* { return ws + (int64_t)(4 + m + slot) * (NQ * T); };
   const int64_t total = A.Nt * (int64_t)A.restarts;
   const bool bounded = A.lower != nullptr;
+  // box bounds padded to NQ entries (the padding is never active)
+  __shared__ double s_lo[NQ], s_hi[NQ];
+  if (threadIdx.x < NQ) {
+    const int j = threadIdx.x;
+    s_lo[j] = (bounded && j < n) ? A.lower[j] : -DBL_MAX;
+    s_hi[j] = (bounded && j < n) ? A.upper[j] : DBL_MAX;
+  }
+  __syncthreads();
 
   int state = AST_IDLE, cur = 0, iter = 0, hcount = 0, hpos = 0, ls = 0;
   bool exhausted = false, slow = false;
@@ -689,10 +714,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
   double f = 0.0, alpha = 1.0, gd = 0.0, gamma = 1.0, f_chk = 0.0;
   double rho[kAdjHist];
   unsigned long long evals = 0;
-  for (int v = 0; v < 4; ++v) {
-    double* p = vecp(v);
-    for (int j = 0; j < n; ++j) p[j * T] = 0.0;  // idle lanes evaluate their (finite) trial buffer
-  }
+  for (int e = 0; e < kVecs * NQ; ++e) ws[e * T] = 0.0;  // padding stays zero; idle lanes evaluate their (finite) trial buffer
 
   while (true) {
     // ---------------- fetch -------------------------------------------------------------------------------
@@ -727,7 +749,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
 
     // ---------------- one loss + gradient evaluation per thread (CTA-convergent) ----------------------------
     double* xt = vecp(2 * (cur ^ 1));
-    double* gt = xt + (int64_t)n * T;
+    double* gt = xt + NQ * T;
     for (int j = 0; j < n; ++j) gt[j * T] = 0.0;
     const double ft = adj1_nl_sync(&kt, xt, T, A.V + t * 32, A.cost_kind, gt, T);
     if (state == AST_IDLE) continue;
@@ -736,20 +758,20 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
 
     // ---------------- bookkeeping (registers; every pass loads first, then computes) -------------------------
     const double* x = vecp(2 * cur);
-    const double* g = x + (int64_t)n * T;
+    const double* g = x + NQ * T;
     const bool first = state == AST_INIT;
     bool done = false;
     int reason = 0;
     // (register budget: at most three NQ-vectors are live at any point -- the evaluation behind the call keeps 255)
     auto load_row = [&](const double* p, double* v) {
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) v[j] = (j < n) ? p[j * T] : 0.0;
+      for (int j = 0; j < NQ; ++j) v[j] = p[j * T];
     };
     auto project = [&](double* gp, const double* xv) {  // drop gradient components pushing against an active bound
       if (bounded) {
 #pragma unroll
         for (int j = 0; j < NQ; ++j)
-          if (j < n && ((xv[j] <= A.lower[j] && gp[j] > 0.0) || (xv[j] >= A.upper[j] && gp[j] < 0.0))) gp[j] = 0.0;
+          if ((xv[j] <= s_lo[j] && gp[j] > 0.0) || (xv[j] >= s_hi[j] && gp[j] < 0.0)) gp[j] = 0.0;
       }
     };
     if (first || ft <= f + kArmijoFd * alpha * gd) {
@@ -779,7 +801,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < NQ; ++j) {
             a[j] -= b[j];  // s
-            if (j < n) sn[j * T] = a[j];
+            sn[j * T] = a[j];
           }
         }
         load_row(gt, q);
@@ -789,7 +811,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < NQ; ++j) {
             const double yv = q[j] - b[j];
-            if (j < n) yn[j * T] = yv;
+            yn[j * T] = yv;
             sy = fma(a[j], yv, sy);
             yy = fma(yv, yv, yy);
           }
@@ -798,7 +820,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
           load_row(xt, b);
 #pragma unroll
           for (int j = 0; j < NQ; ++j)
-            if (j < n && ((b[j] <= A.lower[j] && q[j] > 0.0) || (b[j] >= A.upper[j] && q[j] < 0.0))) {
+            if ((b[j] <= s_lo[j] && q[j] > 0.0) || (b[j] >= s_hi[j] && q[j] < 0.0)) {
               q[j] = 0.0;
               act |= 1u << j;
             }
@@ -886,7 +908,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         load_row(xt, xa);
         load_row(gt, ga);  // (un-projected: the directional derivative along the clamped segment uses it)
         auto gproj = [&](int j) -> double {  // projected gradient component j at the accepted point
-          if (bounded && j < n && ((xa[j] <= A.lower[j] && ga[j] > 0.0) || (xa[j] >= A.upper[j] && ga[j] < 0.0))) return 0.0;
+          if (bounded && ((xa[j] <= s_lo[j] && ga[j] > 0.0) || (xa[j] >= s_hi[j] && ga[j] < 0.0))) return 0.0;
           return ga[j];
         };
         double gdn = 0.0;
@@ -914,13 +936,12 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
           }
           double g_step = 0.0;
 #pragma unroll
-          for (int j = 0; j < NQ; ++j)
-            if (j < n) {
-              double v = fma(alpha, q[j], xa[j]);
-              if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
-              xn[j * T] = v;
-              g_step = fma(ga[j], v - xa[j], g_step);
-            }
+          for (int j = 0; j < NQ; ++j) {
+            double v = fma(alpha, q[j], xa[j]);
+            if (bounded) v = fmin(fmax(v, s_lo[j]), s_hi[j]);
+            xn[j * T] = v;
+            g_step = fma(ga[j], v - xa[j], g_step);
+          }
           gd = g_step / alpha;
           if (gd < 0.0) break;
           if (use_sd) {  // zero (projected) gradient along the steepest-descent step
@@ -982,13 +1003,12 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
           an = fmin(1.0, rsqrt(fmax(gg, 1e-300)));
           load_row(g, dx);  // (un-projected, for the directional derivative)
 #pragma unroll
-          for (int j = 0; j < NQ; ++j)
-            if (j < n) {
-              double v = fma(-an, gv[j], xv[j]);
-              if (bounded) v = fmin(fmax(v, A.lower[j]), A.upper[j]);
-              xt[j * T] = v;
-              g_step = fma(dx[j], v - xv[j], g_step);
-            }
+          for (int j = 0; j < NQ; ++j) {
+            double v = fma(-an, gv[j], xv[j]);
+            if (bounded) v = fmin(fmax(v, s_lo[j]), s_hi[j]);
+            xt[j * T] = v;
+            g_step = fma(dx[j], v - xv[j], g_step);
+          }
           alpha = an;
           gd = g_step / alpha;
           if (!(gd < 0.0)) {
@@ -998,8 +1018,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         } else if (!done) {
           // the segment x -> xt was already inside the box (both ends are), so shrinking it needs no projection
 #pragma unroll
-          for (int j = 0; j < NQ; ++j)
-            if (j < n) xt[j * T] = fma(ratio, dx[j], xv[j]);
+          for (int j = 0; j < NQ; ++j) xt[j * T] = fma(ratio, dx[j], xv[j]);
           alpha = an;
         }
       }
@@ -1051,7 +1070,9 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   const int threads = central == 2 ? kAdjCta : 128;
   int64_t blocks = std::min<int64_t>((int64_t)sms * (256 / threads), (total + threads - 1) / threads);
   // (5 + 2 m) double vectors per thread (the adjoint mode keeps its direction in thread-local memory and uses 4 + 2 m)
-  const size_t per_thread = (size_t)(5 + 2 * kFdHist) * n * sizeof(double);
+  // the register form of the adjoint kernel (P <= 32) pads its vectors to the instantiated bound NQ
+  const int nq = (central == 2 && n <= 32) ? (n <= 16 ? 16 : n <= 24 ? 24 : 32) : n;
+  const size_t per_thread = (size_t)(5 + 2 * kFdHist) * nq * sizeof(double);
   while (blocks > 1 && per_thread * threads * (size_t)blocks > ((size_t)4 << 30)) blocks /= 2;  // workspace <= 4 GiB
   const int64_t T = blocks * threads;
 

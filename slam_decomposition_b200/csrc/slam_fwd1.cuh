@@ -8,7 +8,7 @@
 //         + gz1 A^dag A + gz2 B^dag B                                   (src/slam/hamiltonian.py:114-182)
 // with qutip's create(2) = |1><0|, A = a (x) I, B = I (x) a.  H_s is a general 4x4 Hermitian matrix (no closed
 // form once the phases are non-zero), so each slice is exponentiated by scaling-and-squaring of the degree-16/17
-// cos/sin series of the Hermitian generator (||dt H / 2^s|| <= 0.7 -> truncation < 1e-17), evaluated with triangular
+// cos/sin series of the Hermitian generator (||dt H / 2^s|| <= 0.7 -> truncation < 1e-17), evaluated with 9 triangular
 // products of commuting Hermitian matrices; this replaces qutip's Qobj.expm -> scipy Pade.
 #pragma once
 #include "slam_core.cuh"
@@ -92,7 +92,7 @@ __device__ __forceinline__ void hg_mul(const HermG& A, const HermG& B, HermG& C)
     }
 }
 // Taylor coefficients of cos (a_j = (-1)^j / (2j)!) and sin x / x (b_j = (-1)^j / (2j+1)!), highest power first; the
-// leading sin entry is a zero so that both series run through the same 8-step Horner loop
+// leading sin entry is a zero so that both series run through the same loop
 static __constant__ double kCosSinCoef[9][2] = {
     {1.0 / 20922789888000.0, 0.0},
     {-1.0 / 87178291200.0, -1.0 / 1307674368000.0},
@@ -108,12 +108,12 @@ static __constant__ double kCosSinCoef[9][2] = {
 //
 // exp(-i A) = cos A - i sin A with A = theta H Hermitian, theta = dt / 2^s chosen so that ||A|| <= 0.7:
 //   cos A = sum_{j<=8} a_j K^j,   sin A = A sum_{j<=7} b_j K^j,   K = A^2     (truncation < 1e-17 at ||A|| = 0.7)
-// Both series are Horner recurrences X <- c_j I + K X in ONE runtime loop; every product is between commuting Hermitian
-// matrices, so only upper triangles are formed (~100 FP64 instructions per product instead of 256 dense).  The loop body is
-// ~3.5 KB of code on purpose: the forward-only kernels are instruction-fetch bound (ncu: 70 % I-cache hit rate, stall
-// no_instruction 2.0 per issue with a straight-line Paterson-Stockmeyer variant of the same polynomial), so a compact
-// loop beats a shorter unrolled schedule.  18 triangular products + (s - 1.5) squarings replace 12 dense Horner steps +
-// s squarings of the degree-12 Taylor form used before.
+// Both series are Horner recurrences in K^2 with linear blocks, X <- (c_2i I + c_2i+1 K) + K^2 X (Paterson-Stockmeyer with
+// block size 2), in ONE runtime loop of three steps; every product is between commuting Hermitian matrices, so only upper
+// triangles are formed (~100 FP64 instructions per product instead of 256 dense): 9 triangular products per slice (A A,
+// K K, 3 x 2 in the loop, A P) where the plain Horner form in K needed 18.  The loop body stays ~4 KB on purpose: the
+// forward-only kernels are instruction-fetch sensitive (a straight-line Paterson-Stockmeyer schedule with block size 3 was
+// measured slower than the compact Horner loop last round), and this form keeps the compact loop.
 __device__ __forceinline__ void herm_expm(const Herm4& H, double dt, double rho, cd Y[4][4]) {
   int s = 0;
   if (rho > 0.7) s = min(ilogb(rho * (1.0 / 0.7)) + 1, 40);
@@ -129,30 +129,42 @@ __device__ __forceinline__ void herm_expm(const Herm4& H, double dt, double rho,
   A.u[3] = mkc(theta * H.h12.re, theta * H.h12.im);
   A.u[4] = A.u[1];  // h13 = h02, h23 = h01 (structure of the smush generator)
   A.u[5] = A.u[0];
-  HermG K, C, P;
+  // Horner in K2 = K^2 with linear blocks (Paterson-Stockmeyer, block size 2): a_j = kCosSinCoef[8 - j][0], b_j = ...[1]
+  //   cos:  C <- (a_2i I + a_2i+1 K) + K2 C   from  C = a_6 I + a_7 K + a_8 K2,   i = 2, 1, 0
+  //   sin:  P <- (b_2i I + b_2i+1 K) + K2 P   from  P = b_6 I + b_7 K
+  HermG K, K2, C, P;
   hg_mul(A, A, K);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    C.d[i] = kCosSinCoef[0][0];
-    P.d[i] = 0.0;
-  }
-#pragma unroll
-  for (int e = 0; e < 6; ++e) C.u[e] = P.u[e] = mkc(0.0, 0.0);
-#pragma unroll 1
-  for (int j = 1; j < 9; ++j) {
-    HermG Cn, Pn;
-    hg_mul(K, C, Cn);
-    hg_mul(K, P, Pn);
-    const double a = kCosSinCoef[j][0], b = kCosSinCoef[j][1];
+  hg_mul(K, K, K2);
+  {
+    const double a6 = kCosSinCoef[2][0], a7 = kCosSinCoef[1][0], a8 = kCosSinCoef[0][0];
+    const double b6 = kCosSinCoef[2][1], b7 = kCosSinCoef[1][1];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      C.d[i] = Cn.d[i] + a;
-      P.d[i] = Pn.d[i] + b;
+      C.d[i] = fma(a8, K2.d[i], fma(a7, K.d[i], a6));
+      P.d[i] = fma(b7, K.d[i], b6);
     }
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
-      C.u[e] = Cn.u[e];
-      P.u[e] = Pn.u[e];
+      C.u[e] = mkc(fma(a8, K2.u[e].re, a7 * K.u[e].re), fma(a8, K2.u[e].im, a7 * K.u[e].im));
+      P.u[e] = mkc(b7 * K.u[e].re, b7 * K.u[e].im);
+    }
+  }
+#pragma unroll 1
+  for (int i = 2; i >= 0; --i) {
+    HermG Cn, Pn;
+    hg_mul(K2, C, Cn);
+    hg_mul(K2, P, Pn);
+    const double a0 = kCosSinCoef[8 - 2 * i][0], a1 = kCosSinCoef[7 - 2 * i][0];
+    const double b0 = kCosSinCoef[8 - 2 * i][1], b1 = kCosSinCoef[7 - 2 * i][1];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      C.d[r] = Cn.d[r] + fma(a1, K.d[r], a0);
+      P.d[r] = Pn.d[r] + fma(b1, K.d[r], b0);
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      C.u[e] = mkc(fma(a1, K.u[e].re, Cn.u[e].re), fma(a1, K.u[e].im, Cn.u[e].im));
+      P.u[e] = mkc(fma(b1, K.u[e].re, Pn.u[e].re), fma(b1, K.u[e].im, Pn.u[e].im));
     }
   }
   HermG S;

@@ -44,7 +44,8 @@ int smush_eval_launch(const KTemplate& kt, const double* x, int64_t ldx, double*
 // ---- K2 for parameter-bound smush templates: loss + analytic adjoint gradient, one thread per row -------
 // (replaces objective_func + scipy's (P+1)-evaluation finite-difference gradient for these templates,
 //  optimizer.py:191-214, 270-278)
-template <bool WANT_GRAD>
+// EIG: eigen-form forward sweep handing (Q, lam) of every slice to the backward sweep (slam_adj1.cuh, k T <= kEigSlices)
+template <bool WANT_GRAD, bool EIG = false>
 __global__ void __launch_bounds__(kSmushCta)
 smush_loss_grad_kernel(const double* __restrict__ x, int64_t ldx, const double* __restrict__ V, int64_t Nt,
                        const int32_t* __restrict__ tgt_idx, int cost_kind, double* __restrict__ loss,
@@ -61,7 +62,8 @@ smush_loss_grad_kernel(const double* __restrict__ x, int64_t ldx, const double* 
     RowGrad gs{valid ? grad + b * ldg : nullptr};
     if (valid)
       for (int j = 0; j < kt.P; ++j) gs.row[j] = 0.0;  // parameters bound to no slot keep a zero derivative
-    l = adj1_loss_grad<GlobalParams, RowGrad, kSmushSync>(kt, ps, V + tgt * 32, cost_kind, gs, &T);
+    if (EIG) l = adj1_loss_grad<GlobalParams, RowGrad, kSmushSync, LocalEigStore>(kt, ps, V + tgt * 32, cost_kind, gs, &T);
+    else l = adj1_loss_grad<GlobalParams, RowGrad, kSmushSync>(kt, ps, V + tgt * 32, cost_kind, gs, &T);
   } else {
     l = fwd1_loss<GlobalParams, kSmushSync>(kt, ps, V + tgt * 32, cost_kind, &T);
   }
@@ -77,7 +79,9 @@ int smush_loss_grad_launch(const KTemplate& kt, const double* x, int64_t ldx, co
                            const int32_t* tgt_idx, int cost_kind, double* loss, double* grad, int64_t ldg, double* trace,
                            int64_t B, cudaStream_t st) {
   const unsigned grid = (unsigned)((B + kSmushCta - 1) / kSmushCta);
-  if (grad)
+  if (grad && kt.k * kt.T <= kEigSlices)
+    smush_loss_grad_kernel<true, true><<<grid, kSmushCta, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, kt);
+  else if (grad)
     smush_loss_grad_kernel<true><<<grid, kSmushCta, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, grad, ldg, trace, B, kt);
   else
     smush_loss_grad_kernel<false><<<grid, kSmushCta, 0, st>>>(x, ldx, V, Nt, tgt_idx, cost_kind, loss, nullptr, 0, trace, B, kt);

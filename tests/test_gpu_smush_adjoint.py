@@ -69,7 +69,7 @@ def test_loss_only_and_large_amplitudes():
     Xd, Vd = torch.as_tensor(X, device="cuda"), torch.as_tensor(V, device="cuda")
     l0, _, _ = engine.loss_grad(desc, Xd, Vd, want_grad=False)
     l1, g1, _ = engine.loss_grad(desc, Xd, Vd)
-    assert torch.equal(l0, l1)
+    assert (l0 - l1).abs().max().item() < 1e-13  # (series forward vs eigen-form forward of the gradient launch: rounding only)
     for b in range(8):
         l, g, _ = O.loss_and_grad(orc, X[b], V[b % 3], "basic", h_gate=1e-3, richardson=True)
         assert abs(l1[b].item() - l) < 1e-12
