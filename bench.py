@@ -41,22 +41,23 @@ RESTARTS = 16
 
 # ---- numbers taken from committed ncu captures (profiles/r02_executed_flops.txt lists the reports and the arithmetic) --------
 # dram bytes (read + write) of one lbfgs_kernel launch (k = 3, 1e5 targets x 16 restarts)
-NCU_DRAM_BYTES_K3_LAUNCH = 60_488_960 + 298_873_600
+NCU_DRAM_BYTES_K3_LAUNCH = 61_125_376 + 302_178_304
 # FP64 pipe activity of that launch (sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active)
-NCU_PIPE_FP64_ACTIVE_K5_K3 = 0.590
+NCU_PIPE_FP64_ACTIVE_K5_K3 = 0.624
 # EXECUTED FP64 FLOP per unit = (2 dfma + dmul + dadd thread instructions, smsp__sass_thread_inst_executed_op_*_pred_on) of
-# one launch / the units that launch processed.  The algorithmic model below credits dense 4x4 products the kernels do not
-# execute (Kronecker / block structure, factored U3), so `frac` (algorithmic) overstates pipe use; `frac_executed` does not.
+# one launch / the units that launch processed (scripts/executed_flops.py -> profiles/r02_executed_flops.txt).  The
+# algorithmic model below credits dense 4x4 products the kernels do not execute (Kronecker / block structure, factored U3),
+# so `frac` (algorithmic) overstates pipe use; `frac_executed` does not.
 NCU_EXEC_FLOP = {
-    "k5_eval_k3": 9421.0,          # lbfgs_kernel, k = 3 launch of the sweep: per loss+grad evaluation incl. the L-BFGS bookkeeping
+    "k5_eval_k3": 9300.5,          # lbfgs_kernel, k = 3 launch of the sweep: per loss+grad evaluation incl. the L-BFGS bookkeeping
     "k2_lossgrad_k3": 7834.0,      # loss_grad_kernel<2 lanes>, sqCNOT k = 3, per row
     "k2_lossgrad_k6": 13966.0,     # loss_grad_kernel<4 lanes>, sqCNOT k = 6, per row
-    "k3_weyl": 3597.6,             # weyl_kernel, per Haar matrix
-    "k4b_traj_point": 7687.8,      # trajectory_kernel, per trajectory point (one slice exponential + prefix product + c1c2c3)
-    "k6_plain_sqcnot_k3": 5262.0,  # coverage_kernel, plain template, per sample
-    "k6_smush_sqcnot_k3": 36424.0, # coverage_kernel, parallel-drive template (6 slice exponentials), per sample
-    "k2_smush_lossgrad": 91622.0,  # smush_loss_grad_kernel<grad>, sqrt(iSWAP) k = 3 T = 2 (P = 30), per row
-    "k2_smush_loss": 33153.0,      # smush_loss_grad_kernel<loss only>, per row
+    "k3_weyl": 3597.5,             # weyl_kernel, per Haar matrix
+    "k4b_traj_point": 6260.1,      # trajectory_kernel, per trajectory point (one slice exponential + prefix product + c1c2c3)
+    "k6_plain_sqcnot_k3": 5262.2,  # coverage_kernel, plain template, per sample
+    "k6_smush_sqcnot_k3": 27853.6, # coverage_kernel, parallel-drive template (6 slice exponentials), per sample
+    "k2_smush_lossgrad": 65115.8,  # smush_loss_grad_kernel<grad, eigen-form>, sqrt(iSWAP) k = 3 T = 2 (P = 30), per row
+    "k2_smush_loss": 24587.4,      # smush_loss_grad_kernel<loss only>, per row
 }
 
 
@@ -491,10 +492,10 @@ def run_ours(args):
             "frac_executed_k3": ((k3["evals"] * NCU_EXEC_FLOP["k5_eval_k3"] / (k3["ms"] * 1e-3)) / peak_flops) if k3 and k3["ms"] > 0 else None,
             "executed_flop_per_eval_k3": NCU_EXEC_FLOP["k5_eval_k3"],
             "pipe_fp64_active": NCU_PIPE_FP64_ACTIVE_K5_K3,
-            "pipe_fp64_active_note": "sm__pipe_fp64_cycles_active of the k = 3 launch, ncu --set full (profiles/r02_lbfgs_kernel_ncu_full.txt)",
+            "pipe_fp64_active_note": "sm__pipe_fp64_cycles_active of the k = 3 launch, ncu --set full (profiles/r02_lbfgs_k3_ncu_full.txt)",
             "traffic": NCU_DRAM_BYTES_K3_LAUNCH, "traffic_unit": "bytes/launch",
             "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of the k=3 lbfgs_kernel launch of this workload "
-                             "(1e5 targets x 16 restarts) from one ncu --set full capture, profiles/r02_lbfgs_kernel_ncu_full.txt; "
+                             "(1e5 targets x 16 restarts) from one ncu --set full capture, profiles/r02_lbfgs_k3_ncu_full.txt; "
                              "algorithmic bytes of that launch = result table 1.6e6 x (24+1) x 8 B + iters 6.4 MB = 326 MB "
                              "+ targets 25.6 MB: the kernel is compute bound, DRAM throughput 0.1 % of peak"),
             "peak_source": "slam_fp64_peak: register-resident DFMA loop measured in this run (MEASURED_PEAKS.json has no FP64 entry)",

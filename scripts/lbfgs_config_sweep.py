@@ -20,6 +20,9 @@ from slam_decomposition_b200.utils.gates.custom_gates import ConversionGainGate
 CONFIGS = {
     "auto": {},
     "m4": {"tune_hist_min": 4},
+    "h3": {"history": 3},
+    "h4": {"history": 4},
+    "h5": {"history": 5},
     "w12": {"tune_sm_threads": 384},
     "lpp2": {"tune_lanes": 2},
     "teams96": {"tune_max_teams": 96},

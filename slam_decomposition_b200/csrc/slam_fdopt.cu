@@ -792,6 +792,19 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
             if (act & (1u << j)) q[j] = 0.0;
         }
       };
+      // every history row the two-loop recursion below will read, requested from DRAM now (the workspace of all threads,
+      // > 100 MB, does not stay in L2 across the evaluation): they arrive while the new pair is formed
+      for (int hh = 0; hh < hcount; ++hh) {
+        int slot = hpos - 1 - hh;
+        if (slot < 0) slot += m;
+        const double* ps = hs(slot);
+        const double* py = hy(slot);
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          prefetch_l2(ps + j * T);
+          prefetch_l2(py + j * T);
+        }
+      }
       {
         double a[NQ], b[NQ];
         if (!first) {
@@ -867,8 +880,9 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         for (int hh = 0; hh < hcount; ++hh) {
           int slot = hpos - 1 - hh;
           if (slot < 0) slot += m;
-          double v[NQ];
+          double v[NQ], v2[NQ];
           load_row(hs(slot), v);
+          load_row(hy(slot), v2);  // (issued with the s row: one exposed memory latency per pair instead of two)
           double a0 = 0.0, a1 = 0.0;
 #pragma unroll
           for (int j = 0; j < NQ; j += 2) {
@@ -877,9 +891,8 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
           }
           const double a = (a0 + a1) * rho[slot];
           alp[slot] = a;
-          load_row(hy(slot), v);
 #pragma unroll
-          for (int j = 0; j < NQ; ++j) q[j] = fma(-a, v[j], q[j]);
+          for (int j = 0; j < NQ; ++j) q[j] = fma(-a, v2[j], q[j]);
           mask_q();
         }
         if (hcount > 0) {
@@ -889,8 +902,9 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
         for (int hh = hcount - 1; hh >= 0; --hh) {
           int slot = hpos - 1 - hh;
           if (slot < 0) slot += m;
-          double v[NQ];
+          double v[NQ], v2[NQ];
           load_row(hy(slot), v);
+          load_row(hs(slot), v2);
           double b0 = 0.0, b1 = 0.0;
 #pragma unroll
           for (int j = 0; j < NQ; j += 2) {
@@ -898,9 +912,8 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
             if (j + 1 < NQ) b1 = fma(v[j + 1], q[j + 1], b1);
           }
           const double c = alp[slot] - (b0 + b1) * rho[slot];
-          load_row(hs(slot), v);
 #pragma unroll
-          for (int j = 0; j < NQ; ++j) q[j] = fma(c, v[j], q[j]);
+          for (int j = 0; j < NQ; ++j) q[j] = fma(c, v2[j], q[j]);
           mask_q();
         }
         // d = -q ; g.d with the projected gradient (equals g.d on the free variables)
