@@ -333,6 +333,12 @@ constexpr int kAdjHist = kFdHist;  // (s, y) pairs kept, in double.  Six float p
                                    // workspace against a 126 MB L2) but +21 % evaluations on the near-singular smush
                                    // landscapes and fewer solved targets -- no net gain, so the history stays exact
 
+// how many of the four (x0, g0, x1, g1) vectors of the register-form adjoint kernel fit in shared memory (NQ entries per
+// thread each, 256 threads, 227 KB)
+// all four or none: with three (NQ = 32) the mixed shared / global buffer selection costs more than it saves
+// (sqrt(iSWAP) k = 3, P = 30: 1489 ms against 1310 ms with all four in the global chunk)
+__host__ __device__ constexpr int adj_smem_vecs(int nq) { return 4 * nq * kAdjCta * 8 <= 227 * 1024 ? 4 : 0; }
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int NQ>
@@ -672,15 +678,20 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
 // Measured and rejected on this kernel (scripts/k5c_bench.py, 131072 x 8 restarts, sqiSwap k = 2 / 3 smush templates):
 //   * 2 or 4 CTAs per SM instead of one phase-locked 256-thread CTA (so that one CTA's bookkeeping overlaps another's
 //     evaluation): 98 -> 81 -> 48 M evaluations/s -- the CTA-wide instruction stream through the ~300 KB of code matters more;
-//   * issuing the s and y row of a history pair together and prefetching every row of the two-loop recursion into L2 at the
-//     start of the bookkeeping: no change (2.27 s) -- with 8 warps per SM at 255 registers every warp issues one instruction
-//     per ~7 cycles (ncu: wait 1.9, long_scoreboard 1.2, no_instruction 1.0, barrier 0.7 per issue), so a tick costs the same
-//     ~0.25 ms whether one or all 256 threads are live; the lever is occupancy, which the 4x4 complex R, W, Q of the adjoint
-//     pass (192 registers) do not leave room for.
+//   * prefetching every row of the two-loop recursion into L2 at the start of the bookkeeping: no change, and the burst of
+//     prefetches stalls on the load/store queue (13 % of the stall samples); the s and y row of a pair are issued together.
+// With 8 warps per SM at 255 registers the kernel is bound by latency per warp, not by throughput: a tick costs the same
+// ~0.25 ms whether one or all 256 threads are live.  The lever would be occupancy, which the 4x4 complex R, W, Q of the
+// adjoint pass (192 registers) do not leave room for.
 // ------------------------------------------------------------------------------------------------------------------
 template <int NQ>
 __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_constant__ FdArgs A,
                                                                    const __grid_constant__ KTemplate kt) {
+  // The two (x, g) buffers live in SHARED memory when they fit (4 NQ doubles per thread: NQ <= 28 at 256 threads), only the
+  // (s, y) history in the global chunk: at bench size the workspace of all threads was 145 MB against a 126 MB L2, and ncu
+  // showed the kernel moving 4.7 TB through DRAM in 2.15 s (27 % of peak) with long_scoreboard at 4.4 per issue.
+  constexpr int kSmemVecs = adj_smem_vecs(NQ);
+  extern __shared__ __align__(16) double xg_smem[];
   const int n = kt.P;
   const int m = A.m;
   // CTA-local workspace chunk: vector v of thread t has its entry j at chunk[(v NQ + j) T + t], T = the CTA size -- a
@@ -689,11 +700,15 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
   // passes need no `j < n` guards either.  (With the grid-wide interleave [j T_grid + t] of the local-array form every
   // element cost a 64-bit multiply-add, a compare and a select: ncu had this one line at 19 % of ALL executed instructions.)
   constexpr int64_t T = kAdjCta;
-  constexpr int kVecs = 4 + 2 * kAdjHist;
+  constexpr int kXg = 4 - kSmemVecs;  // (x, g) vectors kept in the global chunk: the last kXg of the four
+  constexpr int kVecs = kXg + 2 * kAdjHist;
   double* ws = A.ws + (int64_t)blockIdx.x * (kVecs * NQ * T) + threadIdx.x;
-  auto vecp = [&](int v) -> double* { return ws + (int64_t)v * (NQ * T); };  // entry j at [j * T]
-  auto hs = [&](int slot) -> double* { return ws + (int64_t)(4 + slot) * (NQ * T); };
-  auto hy = [&](int slot) -> double* { return ws + (int64_t)(4 + m + slot) * (NQ * T); };
+  double* xg = xg_smem + threadIdx.x;
+  auto vecp = [&](int v) -> double* {  // vector v of (x0, g0, x1, g1); entry j at [j * T]
+    return v < kSmemVecs ? xg + (int64_t)v * (NQ * T) : ws + (int64_t)(v - kSmemVecs) * (NQ * T);
+  };
+  auto hs = [&](int slot) -> double* { return ws + (int64_t)(kXg + slot) * (NQ * T); };
+  auto hy = [&](int slot) -> double* { return ws + (int64_t)(kXg + m + slot) * (NQ * T); };
   const int64_t total = A.Nt * (int64_t)A.restarts;
   const bool bounded = A.lower != nullptr;
   // box bounds padded to NQ entries (the padding is never active)
@@ -715,6 +730,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
   double rho[kAdjHist];
   unsigned long long evals = 0;
   for (int e = 0; e < kVecs * NQ; ++e) ws[e * T] = 0.0;  // padding stays zero; idle lanes evaluate their (finite) trial buffer
+  for (int e = 0; e < kSmemVecs * NQ; ++e) xg[e * T] = 0.0;
 
   while (true) {
     // ---------------- fetch -------------------------------------------------------------------------------
@@ -749,7 +765,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
 
     // ---------------- one loss + gradient evaluation per thread (CTA-convergent) ----------------------------
     double* xt = vecp(2 * (cur ^ 1));
-    double* gt = xt + NQ * T;
+    double* gt = vecp(2 * (cur ^ 1) + 1);
     for (int j = 0; j < n; ++j) gt[j * T] = 0.0;
     const double ft = adj1_nl_sync(&kt, xt, T, A.V + t * 32, A.cost_kind, gt, T);
     if (state == AST_IDLE) continue;
@@ -758,7 +774,7 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
 
     // ---------------- bookkeeping (registers; every pass loads first, then computes) -------------------------
     const double* x = vecp(2 * cur);
-    const double* g = x + NQ * T;
+    const double* g = vecp(2 * cur + 1);
     const bool first = state == AST_INIT;
     bool done = false;
     int reason = 0;
@@ -792,19 +808,6 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
             if (act & (1u << j)) q[j] = 0.0;
         }
       };
-      // every history row the two-loop recursion below will read, requested from DRAM now (the workspace of all threads,
-      // > 100 MB, does not stay in L2 across the evaluation): they arrive while the new pair is formed
-      for (int hh = 0; hh < hcount; ++hh) {
-        int slot = hpos - 1 - hh;
-        if (slot < 0) slot += m;
-        const double* ps = hs(slot);
-        const double* py = hy(slot);
-#pragma unroll
-        for (int j = 0; j < NQ; ++j) {
-          prefetch_l2(ps + j * T);
-          prefetch_l2(py + j * T);
-        }
-      }
       {
         double a[NQ], b[NQ];
         if (!first) {
@@ -1048,6 +1051,15 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_reg_kernel(const __grid_
   if (A.out_evals && evals) atomicAdd(A.out_evals, evals);
 }
 
+template <int NQ>
+static int launch_adj_reg(const FdArgs& A, const KTemplate& kt, unsigned blocks, cudaStream_t st) {
+  const size_t smem = (size_t)adj_smem_vecs(NQ) * NQ * kAdjCta * 8;
+  auto kern = adj_lbfgs_reg_kernel<NQ>;
+  if (smem) SLAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<blocks, kAdjCta, smem, st>>>(A, kt);
+  return SLAM_OK;
+}
+
 }  // namespace slam
 
 using namespace slam;
@@ -1084,7 +1096,7 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   int64_t blocks = std::min<int64_t>((int64_t)sms * (256 / threads), (total + threads - 1) / threads);
   // (5 + 2 m) double vectors per thread (the adjoint mode keeps its direction in thread-local memory and uses 4 + 2 m)
   // the register form of the adjoint kernel (P <= 32) pads its vectors to the instantiated bound NQ
-  const int nq = (central == 2 && n <= 32) ? (n <= 16 ? 16 : n <= 24 ? 24 : 32) : n;
+  const int nq = (central == 2 && n <= 32) ? std::max(16, (n + 3) / 4 * 4) : n;  // instantiated: 16, 20, 24, 28, 32
   const size_t per_thread = (size_t)(5 + 2 * kFdHist) * nq * sizeof(double);
   while (blocks > 1 && per_thread * threads * (size_t)blocks > ((size_t)4 << 30)) blocks /= 2;  // workspace <= 4 GiB
   const int64_t T = blocks * threads;
@@ -1116,9 +1128,12 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   A.out_loss = out_loss; A.out_x = out_x; A.out_iters = out_iters; A.out_evals = out_evals;
   A.next = next; A.solved = solved; A.ws = ws; A.T = T;
   if (central == 2) {
-    if (n <= 16) adj_lbfgs_reg_kernel<16><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
-    else if (n <= 24) adj_lbfgs_reg_kernel<24><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
-    else if (n <= 32) adj_lbfgs_reg_kernel<32><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
+    if (n <= 16) rc = launch_adj_reg<16>(A, kt, (unsigned)blocks, st);
+    else if (n <= 20) rc = launch_adj_reg<20>(A, kt, (unsigned)blocks, st);
+    else if (n <= 24) rc = launch_adj_reg<24>(A, kt, (unsigned)blocks, st);
+    else if (n <= 28) rc = launch_adj_reg<28>(A, kt, (unsigned)blocks, st);
+    else if (n <= 32) rc = launch_adj_reg<32>(A, kt, (unsigned)blocks, st);
+    if (rc != SLAM_OK) return rc;
     // (a 48-entry register form was measured: 3.8 KB of spills around the 255-register evaluation, 6.3 vs 7.6 M evaluations/s
     //  on the sqCNOT k = 4 template, P = 42 -- the local-array form keeps the larger templates)
     else if (n <= 96) adj_lbfgs_kernel<96><<<(unsigned)blocks, threads, 0, st>>>(A, kt);
