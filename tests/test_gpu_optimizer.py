@@ -353,6 +353,33 @@ def test_chained_sweep_matches_the_sequential_k_loop():
         assert abs(O.cost(tmpl.eval(a["Xk"][i, : tmpl.n_params]), V[i], "basic") - a["loss"][i]) < 1e-10
 
 
+def test_repeated_chained_sweeps_reuse_descriptors_and_notice_a_changed_basis():
+    """Second and later chained sweeps of one optimizer queue their launches from cached template descriptors and run the
+    template builds afterwards (overlapped with the kernels); the builds still happen -- the basis ends built at the last
+    size, as after the reference's k-loop -- and a basis that was modified in between is noticed (fresh descriptors are
+    compared with the cached ones) and the sweep repeated with the new templates."""
+    from slam_decomposition_b200.utils.gates.custom_gates import RiSwapGate
+    rng = np.random.default_rng(5)
+    V = np.stack([O.haar_unitary(rng) for _ in range(200)] + [O.CNOT]).astype(np.complex128)
+    basis = CircuitTemplate(base_gates=[RiSwapGate(1 / 2)], maximum_span_guess=4, preseed=False)
+    opt = TemplateOptimizer(basis=basis, objective=BasicCost(), override_fail=True, training_restarts=6)
+    first = opt.approximate_targets(V, range(1, 5), reuse_host_buffers=False)
+    assert opt._desc_cache and basis.desc.k == 4
+    second = opt.approximate_targets(V, range(1, 5), reuse_host_buffers=False)
+    assert basis.desc.k == 4
+    for out in (first, second):
+        assert (out["success"] == 1).all() and out["cycles"][-1] == 2 and out["cycles"][:-1].max() <= 3
+    # change the basis gate behind the optimizer's back: CNOT is one application of a full iSWAP-family gate away at k = 2,
+    # but with RiSwap(1/4) the generic targets need more applications -- the cached descriptors must not be used
+    basis.gate_2q_base.items[0] = RiSwapGate(1 / 4)
+    third = opt.approximate_targets(V, range(1, 5), reuse_host_buffers=False)
+    k = int(third["cycles"][0])
+    tmpl = O.OracleTemplate("riswap", (0.25,), k=k)
+    if third["success"][0]:
+        assert abs(O.cost(tmpl.eval(third["Xk"][0, : tmpl.n_params]), V[0], "basic") - third["loss"][0]) < 1e-10
+    assert third["cycles"][:-1].mean() > second["cycles"][:-1].mean()
+
+
 def test_packed_key_reduction_equals_the_reduction_of_the_restart_tables():
     """SlamOptOpts.best_key + slam_best_gather: the per-target reduction K5 feeds with one atomic minimum per retired restart
     (the merge of optimizer.py:283-303) must pick what a host-side reduction of the per-restart tables picks -- for one
