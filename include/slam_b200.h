@@ -151,7 +151,7 @@ int slam_weyl(const double* U, int64_t B, double* c, double* g, int32_t flags, v
 typedef struct SlamOptOpts {
   int32_t max_iter;      /* per restart; reference: options={"maxiter": 2500}                    */
   int32_t history;       /* L-BFGS pairs kept (<= 8); 0 = auto (slam_lbfgs_solve: from the shared-memory budget;
-                            slam_fd_lbfgs_solve adjoint mode: 8 for P <= 32, else 5; its finite-difference modes always keep 8)           */
+                            slam_fd_lbfgs_solve adjoint mode: 8 for P <= 20, 6 for P <= 32, else 5; its finite-difference modes always keep 8)           */
   int32_t cost_kind;     /* SlamCostKind                                                         */
   int32_t early_exit;    /* 1: other restarts of a target stop once one is < success_threshold   */
   double success_threshold; /* reference SUCCESS_THRESHOLD = 1e-10 (optimizer.py:18)             */

@@ -1114,11 +1114,13 @@ extern "C" int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V
   A.max_iter = opts->max_iter; A.cost_kind = opts->cost_kind; A.early_exit = opts->early_exit; A.central = central;
   // smush gates carry no circuit_fidelity factor, so 1 - BasicCostInverse x 1 is BasicCost (optimizer.py:200-201)
   if (central == 2 && A.cost_kind == SLAM_COST_BASIC_INVERSE) A.cost_kind = SLAM_COST_BASIC;
-  // history of the adjoint kernels, measured (scripts/k5c_bench.py, 131072 x 8 restarts; scripts/k5c_basin_check.py): for P <= 32
-  // (register form) 8 -> 6 pairs is flat to 12 % faster but costs 7 - 9 % more evaluations and, on the singular-Hessian
-  // in-basin problem of the tests, 2 of 12 targets no longer reach 1e-10 -- 8 stays; for the local-array form (P = 42) 5 pairs
-  // are 16 % faster than 8 at an unchanged solved fraction
-  A.m = opts->history > 0 ? std::min<int>(opts->history, kAdjHist) : (n <= 32 ? kAdjHist : 5);
+  // history of the adjoint kernels, measured (scripts/k5c_bench.py, 131072 x 8 restarts; scripts/k5c_basin_check.py;
+  // scripts/smush_training_grid.py): at P = 18 eight pairs are needed -- with six, 2 of the 12 targets of the
+  // singular-Hessian in-basin problem of the tests no longer reach 1e-10 and the run is no faster; at P = 22 .. 30 six pairs
+  // are 10 - 14 % faster (7 - 9 % more evaluations, each cheaper; the history is what misses L2) at unchanged solved
+  // fractions (0.994 on sqrt(iSWAP) k = 3, 0.98 / 0.99 on the configs[3] grid); the local-array form (P = 42) is 16 % faster
+  // with five than with eight
+  A.m = opts->history > 0 ? std::min<int>(opts->history, kAdjHist) : (n <= 20 ? kAdjHist : n <= 32 ? 6 : 5);
   A.debug = opts->diag;  // stop-reason / evaluation-count packing in out_iters (see SlamOptOpts.diag)
   A.success_threshold = opts->success_threshold; A.f_stop = opts->f_stop; A.gtol = opts->gtol;
   A.gtol_far = opts->gtol_far; A.f_far = opts->f_far; A.x0_lo = opts->x0_lo; A.x0_span = opts->x0_hi - opts->x0_lo;
