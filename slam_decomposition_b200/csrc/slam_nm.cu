@@ -10,8 +10,8 @@
 //
 // One thread per problem (the objective is forward-only and cheap; there is no shuffle-level parallelism to gain),
 // persistent grid with a global work counter, restart-major order with early exit like K5.  The simplex lives in
-// a global-memory workspace interleaved across threads (element e of thread t at ws[e * T + t]) so every vector
-// operation is a coalesced stream.  A tick-structured, phase-locked form of this kernel (one objective evaluation per
+// a global-memory workspace interleaved across the threads of a CTA (element e of thread t at chunk[e * 128 + t]) so
+// every vector operation is a coalesced stream.  A tick-structured, phase-locked form of this kernel (one objective evaluation per
 // thread per tick, as in the adjoint K5c kernel) was written and measured: bit-identical results, but 183 against 208 M
 // objective evaluations/s on 131072 x 4 Makhlin problems (sqrt(iSWAP) k=3) -- a simplex step is one or two cheap evaluations
 // between O(n) vector updates, so the CTA-wide barrier per evaluation costs more than the divergence it removes -- and dropped.
@@ -40,19 +40,22 @@ struct NmArgs {
   unsigned long long* out_evals;
   unsigned long long* next;
   int32_t* solved;
-  double* ws;   // workspace: (n + 5) vectors of n doubles + (n + 1) function values per thread, interleaved
-  int64_t T;    // threads in the grid (interleave stride)
+  double* ws;   // workspace: (n + 4) vectors of n doubles + (n + 1) function values per thread, interleaved per CTA
+  int64_t T;    // threads in the grid
 };
 
 __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs A, const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
-  const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t T = A.T;
-  double* ws = A.ws + tidg;
+  // CTA-local interleave: element e of thread t of this CTA at chunk[e * 128 + t] -- still one coalesced line per warp
+  // access, and the element index is 32-bit arithmetic with a constant stride (with the grid-wide stride A.T every access
+  // cost a 64-bit multiply; in the K5c adjoint kernel that addressing was 19 % of all executed instructions)
+  constexpr int T = 128;
+  const int per_thread = (n + 4) * n + (n + 1);
+  double* ws = A.ws + (int64_t)blockIdx.x * ((int64_t)per_thread * T) + threadIdx.x;
   // workspace vectors (each n entries, entry j at [(vec * n + j) * T]): simplex vertices 0..n, then xr, xe/xc, sum
-  auto vec = [&](int v, int j) -> double& { return ws[((int64_t)v * n + j) * T]; };
+  auto vec = [&](int v, int j) -> double& { return ws[(v * n + j) * T]; };
   const int V_XR = n + 1, V_XT = n + 2, V_SUM = n + 3;
-  double* fs = ws + (int64_t)(n + 4) * n * T;  // fs[v * T], v = 0..n
+  double* fs = ws + (n + 4) * n * T;  // fs[v * T], v = 0..n
   const int64_t total = A.Nt * (int64_t)A.restarts;
   unsigned long long evals = 0;
 
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs 
       for (int v = 0; v <= n; ++v) s += vec(v, j);
       vec(V_SUM, j) = s;
     }
-    for (int v = 0; v <= n; ++v) fs[(int64_t)v * T] = f_at(v);
+    for (int v = 0; v <= n; ++v) fs[v * T] = f_at(v);
 
     int iter = 0;
     int ib = 0;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs 
       int iw = 0;
       double fb = DBL_MAX, fw = -DBL_MAX, f2 = -DBL_MAX;
       for (int v = 0; v <= n; ++v) {
-        const double f = fs[(int64_t)v * T];
+        const double f = fs[v * T];
         if (f < fb) { fb = f; ib = v; }
         if (f > fw) { f2 = fw; fw = f; iw = v; }
         else if (f > f2) { f2 = f; }
@@ -158,12 +161,12 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs 
           vec(V_SUM, j) += xn - xw;
           vec(iw, j) = xn;
         }
-        fs[(int64_t)iw * T] = ftake;
+        fs[iw * T] = ftake;
       } else {
         for (int v = 0; v <= n; ++v) {
           if (v == ib) continue;
           for (int j = 0; j < n; ++j) vec(v, j) = vec(ib, j) + 0.5 * (vec(v, j) - vec(ib, j));
-          fs[(int64_t)v * T] = f_at(v);
+          fs[v * T] = f_at(v);
         }
         for (int j = 0; j < n; ++j) {
           double s = 0.0;
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(128) nm_kernel(const __grid_constant__ NmArgs 
         }
       }
     }
-    const double fbest = fs[(int64_t)ib * T];
+    const double fbest = fs[ib * T];
     A.out_loss[pid] = fbest;
     A.out_iters[pid] = iter;
     for (int j = 0; j < n; ++j) A.out_x[pid * n + j] = vec(ib, j);
