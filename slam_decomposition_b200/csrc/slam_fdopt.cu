@@ -345,9 +345,9 @@ template <int NQ>
 __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_constant__ FdArgs A, const __grid_constant__ KTemplate kt) {
   const int n = kt.P;
   const int m = A.m;
-  const int64_t tidg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t T = A.T;
-  double* ws = A.ws + tidg;
+  // CTA-local interleave of the workspace (entry j of a vector of thread t at [j * 256 + t]): constant stride, 32-bit indices
+  constexpr int64_t T = kAdjCta;
+  double* ws = A.ws + (int64_t)blockIdx.x * ((int64_t)(5 + 2 * kFdHist) * n * T) + threadIdx.x;
   auto vecp = [&](int v) -> double* { return ws + (int64_t)v * n * T; };  // entry j at [j * T]
   // history behind the four (x, g) vectors: pair slot i at hs(i) / hy(i), entry j at [j * T]
   auto hs = [&](int slot) -> double* { return ws + (int64_t)(4 + slot) * n * T; };
