@@ -758,6 +758,25 @@ def micro_benchmarks(engine, peak_flops):
     t = _timed(k5c, reps=1, warm=1)
     out["k5c_smush_adjoint_lbfgs"] = {"loss_grad_evals_per_s": int(ev.item()) / t, "ms": 1e3 * t, "params": b2.desc.n_params,
                                       "problems": n_k5c * 8}
+
+    # K5b: batched Nelder-Mead on the Makhlin functional (the coordinate-based costs and the pulse searches run on it)
+    from slam_decomposition_b200 import _lib
+    from slam_decomposition_b200.basis import CircuitTemplate as _CT
+    from slam_decomposition_b200.utils.gates.custom_gates import RiSwapGate
+
+    b3 = _CT(base_gates=[RiSwapGate(1 / 2)], maximum_span_guess=3, preseed=False)
+    b3.build(3)
+    Vn = torch.as_tensor(haar_targets(131072, 9), device=dev)
+    nm = engine.nm_defaults()
+    nm.cost_kind = _lib.COST_MAKHLIN_FUNCTIONAL
+
+    def k5b():
+        ev.zero_()
+        engine.nm_solve(b3.desc, Vn, 4, nm, seed=3, evals=ev)
+
+    t = _timed(k5b, reps=1, warm=1)
+    out["k5b_nelder_mead_makhlin"] = {"objective_evals_per_s": int(ev.item()) / t, "ms": 1e3 * t, "params": b3.desc.n_params,
+                                      "problems": 131072 * 4}
     return out
 
 
