@@ -15,6 +15,7 @@ namespace slam {
 // barrier makes every warp wait for the slowest row; with the rows staged through shared memory first it was still slower
 // (554 vs 656 and 167 vs 184: the warps of a one-shot streaming kernel start in step anyway, the barriers only add waits) --
 // so SYNC stays off; padding lanes still recompute the last row so that the flag can be flipped for experiments.
+// (Re-measured in round 2 for the eigen-form gradient kernel: 326 vs 330 and 211 vs 209 M rows/s at k = 2 / 3 -- no difference.)
 constexpr int kSmushCta = 128;
 constexpr bool kSmushSync = false;
 
