@@ -260,7 +260,9 @@ int slam_best_gather(const unsigned long long* best_key, int64_t Nt, int32_t res
  *   central = 0: forward differences (scipy's jac=None);  1: central differences (2P evaluations per gradient, step 6e-6);
  *   central = 2: ANALYTIC adjoint gradient through the smush slices (as slam_loss_grad; smush templates only, else
  *                SLAM_ERR_UNSUPPORTED): one backward pass (~3 forward evaluations of work) instead of P + 1 evaluations.
- * Box bounds (opts->lower/upper) by projection; the trace fields of opts are ignored.  Other arguments as
+ * Box bounds (opts->lower/upper) by projection (adjoint mode: the quasi-Newton direction is computed in the free subspace of
+ * the current active set, with a projected steepest-descent fallback; a restart ends on a bound only at a KKT point); the
+ * trace fields of opts are ignored; opts->history and opts->diag apply (see SlamOptOpts).  Other arguments as
  * slam_lbfgs_solve; out_evals counts forward evaluations (one per gradient when central = 2).
  */
 int slam_fd_lbfgs_solve(const SlamTemplateDesc* desc, const double* V, int64_t Nt, int32_t restarts,
