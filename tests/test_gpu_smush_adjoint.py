@@ -208,3 +208,35 @@ def test_bounded_adjoint_run_stops_only_at_kkt_points():
         assert np.abs(g_ * free).max() < 1e-6
     assert (reason == 7).mean() < 0.05, np.bincount(reason)
     assert (loss.min(dim=1).values <= 1e-9).float().mean().item() >= 0.75
+
+
+@pytest.mark.parametrize("gc,gg,t,k,form", [
+    (np.pi / 2, 0.0, 0.25, 2, "reg16"),   # P = 14
+    (np.pi / 2, 0.0, 0.5, 2, "reg20"),    # P = 18
+    (np.pi / 2, 0.0, 0.75, 2, "reg24"),   # P = 22
+    (np.pi / 4, np.pi / 4, 1.0, 2, "reg28"),  # P = 26
+    (np.pi / 2, 0.0, 0.5, 3, "reg32"),    # P = 30
+    (np.pi / 4, np.pi / 4, 0.5, 4, "local-array"),  # P = 42
+])
+def test_every_form_of_the_adjoint_optimizer_converges_in_the_basin(gc, gg, t, k, form):
+    """K5c's adjoint mode picks a kernel by parameter count -- register form with the vector bound NQ = 16 / 20 / 24 / 28 / 32
+    ((x, g) buffers in shared memory up to 28), local-array form above 32.  Each must solve in-basin starts of the
+    parallel-drive Monte-Carlo template (parallel_drive_volume.py:175-199) and return parameters that reproduce the loss."""
+    T = round(t / 0.25)
+    basis = pdv.smush_template(gc, gg, t, k)
+    orc = O.OracleTemplate("smush", ("Q", "Q", gc, gg) + ("Q",) * (2 * T) + (t,), k=k, T=T, no_exterior_1q=True)
+    P = orc.n_params
+    assert basis.desc.n_params == P
+    rng = np.random.default_rng(zlib.crc32(form.encode()))
+    Nt, R = 24, 2
+    X_true = rng.uniform(-1.2, 1.2, (Nt, P))
+    V = torch.as_tensor(np.stack([orc.eval(x) for x in X_true]), device="cuda")
+    x0 = torch.as_tensor(X_true[:, None, :] + 0.05 * rng.standard_normal((Nt, R, P)), device="cuda")
+    opts = engine.opt_defaults()
+    opts.f_far = 1e-4
+    loss, x, _ = engine.fd_lbfgs_solve(basis.desc, V, R, opts, x0=x0, central="adjoint")
+    best = loss.min(dim=1).values.cpu().numpy()
+    assert (best <= 1e-9).mean() >= 0.9, (form, np.sort(best)[-4:])
+    i = int(np.argmin(best))
+    r = int(loss[i].argmin().item())
+    assert abs(O.cost(orc.eval(x[i, r].cpu().numpy()), V[i].cpu().numpy(), "basic") - best[i]) < 1e-10
