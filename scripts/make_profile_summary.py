@@ -13,7 +13,8 @@ METRICS = [
     'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed',
     'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed',
     'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
-    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum',
+    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores',
+    'l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct',
     'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
