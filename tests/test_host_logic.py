@@ -192,3 +192,27 @@ def test_hull_coverage_reproduces_the_reference_base_volume_of_two_sqrt_iswaps()
     # the reference's recorded table is shipped as a golden fixture for the GPU-side comparison
     tab = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "extended_results.json")))
     assert tab["sqiSwap"]["2"][0] == ref
+
+
+def test_descriptor_cache_key_follows_the_gate_cycle_phase():
+    """TemplateOptimizer caches the template descriptors of a repeated chained sweep under (basis, sizes, gate-cycle phase).
+    The reference's gate cycles keep advancing across builds (basis.py:68-72): with one base gate the phase never changes
+    (cache hit on the next sweep), with two it depends on how many gates earlier builds consumed -- and a build from a
+    different phase really yields a different descriptor."""
+    from slam_decomposition_b200.optimizer import TemplateOptimizer
+
+    one = CircuitTemplate(base_gates=[RiSwapGate(1 / 2)], maximum_span_guess=3, preseed=False)
+    p0 = TemplateOptimizer._cycle_phase(one)
+    one.build(3)
+    d1 = bytes(one.desc)
+    assert TemplateOptimizer._cycle_phase(one) == p0
+    one.build(3)
+    assert bytes(one.desc) == d1
+
+    two = CircuitTemplate(base_gates=[RiSwapGate(1 / 2), RiSwapGate(1 / 3)], maximum_span_guess=3, preseed=False)
+    q0 = TemplateOptimizer._cycle_phase(two)
+    two.build(3)  # consumes three gates of a cycle of two: the phase moves
+    e1 = bytes(two.desc)
+    assert TemplateOptimizer._cycle_phase(two) != q0
+    two.build(3)
+    assert bytes(two.desc) != e1
