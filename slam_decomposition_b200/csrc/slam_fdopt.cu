@@ -679,7 +679,9 @@ __global__ void __launch_bounds__(kAdjCta, 1) adj_lbfgs_kernel(const __grid_cons
 //   * 2 or 4 CTAs per SM instead of one phase-locked 256-thread CTA (so that one CTA's bookkeeping overlaps another's
 //     evaluation): 98 -> 81 -> 48 M evaluations/s -- the CTA-wide instruction stream through the ~300 KB of code matters more;
 //   * prefetching every row of the two-loop recursion into L2 at the start of the bookkeeping: no change, and the burst of
-//     prefetches stalls on the load/store queue (13 % of the stall samples); the s and y row of a pair are issued together.
+//     prefetches stalls on the load/store queue (13 % of the stall samples); the s and y row of a pair are issued together;
+//   * a persisting L2 access-policy window over the history chunk (79 MB set-aside, the rest streaming): 1.82 -> 2.05 s (P = 18)
+//     and 1.37 -> 1.66 s (P = 30) -- the thread-local traffic of the evaluation needs the L2 as much as the history does.
 // With 8 warps per SM at 255 registers the kernel is bound by latency per warp, not by throughput: a tick costs the same
 // ~0.25 ms whether one or all 256 threads are live.  The lever would be occupancy, which the 4x4 complex R, W, Q of the
 // adjoint pass (192 registers) do not leave room for.
